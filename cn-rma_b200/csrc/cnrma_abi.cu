@@ -1,0 +1,228 @@
+// extern "C" surface of libcnrma_b200.so (include/cnrma_b200.h): argument validation and launches.
+// No torch types, no allocation, no global state beyond a thread-local last-CUDA-error slot.
+#include <cmath>
+#include <cstdlib>
+
+#include "cnrma_internal.cuh"
+
+namespace cnrma {
+
+static thread_local int g_last_cuda_error = 0;
+
+static int fail_cuda(cudaError_t e) {
+    g_last_cuda_error = (int)e;
+    return CNRMA_ERR_CUDA;
+}
+
+static bool grid_ok(const cnrma_grid *g) {
+    if (!g || g->nx <= 0 || g->ny <= 0 || g->nz <= 0) return false;
+    if (!(g->voxel_size > 0.0f)) return false;
+    return (int64_t)g->nx * g->ny * g->nz < (int64_t)1 << 31;
+}
+
+static int features_ok(const cnrma_features *f, bool need_channels_last, bool allow_empty = false) {
+    if (f && allow_empty && f->views == 0 && f->channels > 0 && (f->dtype == CNRMA_F32 || f->dtype == CNRMA_BF16))
+        return f->channels % ((f->dtype == CNRMA_BF16) ? 8 : 4) == 0 ? CNRMA_OK : CNRMA_ERR_LAYOUT;
+    if (!f || !f->view_ptrs_host || f->views <= 0 || f->channels <= 0 || f->height <= 0 || f->width <= 0)
+        return CNRMA_ERR_ARG;
+    if (f->dtype != CNRMA_F32 && f->dtype != CNRMA_BF16) return CNRMA_ERR_ARG;
+    for (int v = 0; v < f->views; ++v)
+        if (!f->view_ptrs_host[v]) return CNRMA_ERR_ARG;
+    if ((int64_t)f->height * f->stride_y + (int64_t)f->width * f->stride_x >= (int64_t)1 << 31) return CNRMA_ERR_UNSUPPORTED;
+    if (need_channels_last) {
+        const int e = (f->dtype == CNRMA_BF16) ? 8 : 4;
+        if (f->stride_c != 1 || f->channels % e != 0 || f->stride_x % e != 0 || f->stride_y % e != 0)
+            return CNRMA_ERR_LAYOUT;
+        for (int v = 0; v < f->views; ++v)
+            if (reinterpret_cast<uintptr_t>(f->view_ptrs_host[v]) % 16 != 0) return CNRMA_ERR_LAYOUT;
+    }
+    return CNRMA_OK;
+}
+
+static int device_ok() {
+    int dev = 0, major = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail_cuda(e);
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) return fail_cuda(e);
+    return major == 10 ? CNRMA_OK : CNRMA_ERR_DEVICE;
+}
+
+}  // namespace cnrma
+
+using namespace cnrma;
+
+extern "C" {
+
+int cnrma_abi_version(void) { return CNRMA_ABI_VERSION; }
+
+const char *cnrma_status_string(int status) {
+    switch (status) {
+        case CNRMA_OK: return "ok";
+        case CNRMA_ERR_ARG: return "invalid argument";
+        case CNRMA_ERR_LAYOUT: return "feature maps must be channels-last and 16-byte aligned (see cnrma_to_channels_last)";
+        case CNRMA_ERR_CAPACITY: return "output buffer or workspace too small";
+        case CNRMA_ERR_DEVICE: return "CUDA device is not compute capability 10.x (B200)";
+        case CNRMA_ERR_CUDA: return "CUDA runtime error (see cnrma_last_cuda_error)";
+        case CNRMA_ERR_UNSUPPORTED: return "unsupported shape";
+    }
+    return "unknown status";
+}
+
+int cnrma_last_cuda_error(void) { return g_last_cuda_error; }
+
+int cnrma_check_device(void) { return device_ok(); }
+
+int cnrma_project_views(const cnrma_grid *grid, const float *projections, int64_t proj_view_stride, int views,
+                        float stride, int height, int width, int32_t *px, int32_t *py, uint8_t *valid, void *stream) {
+    if (!grid_ok(grid) || !projections || views <= 0 || height <= 0 || width <= 0 || !(stride > 0.0f))
+        return CNRMA_ERR_ARG;
+    if (views > 65535) return CNRMA_ERR_UNSUPPORTED;
+    const int d = device_ok();
+    if (d != CNRMA_OK) return d;
+    const cudaError_t e = run_project_views(to_dev(*grid), projections, proj_view_stride, views, stride, height, width,
+                                            px, py, valid, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
+}
+
+int cnrma_aggregate_views(const cnrma_grid *grid, const cnrma_features *features, const float *projections,
+                          int64_t proj_view_stride, float stride, uint32_t flags, float *volume,
+                          int64_t vol_stride_voxel, int64_t vol_stride_channel, int32_t *count, uint8_t *valid,
+                          void *stream) {
+    if (!grid_ok(grid) || !features || !volume || !count || !(stride > 0.0f)) return CNRMA_ERR_ARG;
+    if (!projections && features->views > 0) return CNRMA_ERR_ARG;
+    if (flags & ~(CNRMA_AGG_ACCUMULATE | CNRMA_AGG_MEAN | CNRMA_AGG_COUNT_F32)) return CNRMA_ERR_ARG;
+    const int fs = features_ok(features, true, (flags & CNRMA_AGG_ACCUMULATE) != 0);
+    if (fs != CNRMA_OK) return fs;
+    const int d = device_ok();
+    if (d != CNRMA_OK) return d;
+    // Tuning knob (DESIGN.md "K_A"): cap on 16-byte vectors per channel pass; 0 = whole rows in one pass.
+    int max_chunk_vecs = 0;
+    if (const char *env = std::getenv("CNRMA_AGG_CHUNK_VECS")) max_chunk_vecs = std::atoi(env);
+    const GridDev g = to_dev(*grid);
+    for (int v0 = 0; v0 < features->views || v0 == 0; v0 += kMaxViewsPerLaunch) {
+        const int nv = (features->views - v0 < kMaxViewsPerLaunch) ? (features->views - v0) : kMaxViewsPerLaunch;
+        uint32_t fl = flags & (CNRMA_AGG_ACCUMULATE | CNRMA_AGG_COUNT_F32);
+        if (v0 > 0) fl |= CNRMA_AGG_ACCUMULATE;
+        if ((flags & CNRMA_AGG_MEAN) && v0 + nv == features->views) fl |= CNRMA_AGG_MEAN;
+        const cudaError_t e = run_aggregate_views(g, *features, v0, nv, projections + (int64_t)v0 * proj_view_stride,
+                                                  proj_view_stride, stride, fl, volume, vol_stride_voxel,
+                                                  vol_stride_channel, count, valid, max_chunk_vecs,
+                                                  static_cast<cudaStream_t>(stream));
+        if (e != cudaSuccess) return fail_cuda(e);
+    }
+    return CNRMA_OK;
+}
+
+int cnrma_to_channels_last(const cnrma_features *src, void *dst, void *stream) {
+    const int fs = features_ok(src, false);
+    if (fs != CNRMA_OK) return fs;
+    if (!dst) return CNRMA_ERR_ARG;
+    const int d = device_ok();
+    if (d != CNRMA_OK) return d;
+    const size_t esz = (src->dtype == CNRMA_BF16) ? 2 : 4;
+    const size_t per_view = (size_t)src->height * src->width * src->channels * esz;
+    for (int v = 0; v < src->views; ++v) {
+        const cudaError_t e = run_to_channels_last(src->view_ptrs_host[v], src->dtype, src->channels, src->height,
+                                                   src->width, src->stride_c, src->stride_y, src->stride_x,
+                                                   static_cast<unsigned char *>(dst) + (size_t)v * per_view,
+                                                   static_cast<cudaStream_t>(stream));
+        if (e != cudaSuccess) return fail_cuda(e);
+    }
+    return CNRMA_OK;
+}
+
+float cnrma_t_one(const cnrma_grid *grid, double voxel_size, int grids) {
+    // rm.py:710-711: sqrt(X**2 + Y**2 + Z**2) * voxel_size / N in python doubles; `arange * t_one` then
+    // multiplies by the value rounded to float.
+    const double x = grid->nx, y = grid->ny, z = grid->nz;
+    return (float)(std::sqrt(x * x + y * y + z * z) * voxel_size / (double)grids);
+}
+
+int cnrma_ray_parameters(const float *pinv, int views, int height, int width, float *o, float *d, void *stream) {
+    if (!pinv || !o || !d || views <= 0 || height <= 0 || width <= 0) return CNRMA_ERR_ARG;
+    const int dv = device_ok();
+    if (dv != CNRMA_OK) return dv;
+    const cudaError_t e = run_ray_parameters(pinv, views, height, width, o, d, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
+}
+
+int cnrma_rma_workspace_bytes(int views, int height, int width, int grids, int mode, float threshold,
+                              int depth_points, size_t *bytes) {
+    if (!bytes || views <= 0 || height <= 0 || width <= 0 || grids <= 0) return CNRMA_ERR_ARG;
+    if (mode != CNRMA_MARCH_NEUS && mode != CNRMA_MARCH_DEPTH) return CNRMA_ERR_ARG;
+    if (mode == CNRMA_MARCH_DEPTH && depth_points < 0) return CNRMA_ERR_ARG;
+    *bytes = rma_workspace(views, height, width, grids, mode, threshold, depth_points).total;
+    return CNRMA_OK;
+}
+
+int cnrma_rma_march(const cnrma_grid *grid, const float *pinv, int views, int height, int width, const float *tsdf,
+                    int grids, float t_one, int mode, float threshold, int depth_points, void *workspace,
+                    size_t workspace_bytes, cnrma_rma_result *result, void *stream) {
+    if (!grid_ok(grid) || !pinv || !tsdf || !workspace || !result) return CNRMA_ERR_ARG;
+    size_t need = 0;
+    const int s = cnrma_rma_workspace_bytes(views, height, width, grids, mode, threshold, depth_points, &need);
+    if (s != CNRMA_OK) return s;
+    if (workspace_bytes < need) return CNRMA_ERR_CAPACITY;
+    if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) return CNRMA_ERR_LAYOUT;
+    const int d = device_ok();
+    if (d != CNRMA_OK) return d;
+    const RmaWorkspace ws = rma_workspace(views, height, width, grids, mode, threshold, depth_points);
+    if (ws.blocks >= ((int64_t)1 << 31)) return CNRMA_ERR_UNSUPPORTED;
+    const cudaError_t e = run_march(to_dev(*grid), pinv, views, height, width, tsdf, grids, t_one, mode, threshold,
+                                    depth_points, workspace, ws, result, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
+}
+
+// fill / scatter share one launcher; the workspace layout is re-derived from the same capacity-defining
+// arguments (grids, mode, threshold, depth_points) the march call was given.
+static int fill_common(const cnrma_grid *grid, const float *pinv, const cnrma_features *features, int grids,
+                       float t_one, int mode, float threshold, int depth_points, const void *workspace, int normalize,
+                       const float *mean, float *rows, int64_t row_stride, float *wsum, float *wtot, void *stream) {
+    if (!grid_ok(grid) || !pinv || !workspace) return CNRMA_ERR_ARG;
+    const int fs = features_ok(features, false);
+    if (fs != CNRMA_OK) return fs;
+    if (features->stride_c != 1) return CNRMA_ERR_LAYOUT;
+    const int d = device_ok();
+    if (d != CNRMA_OK) return d;
+    const RmaWorkspace ws = rma_workspace(features->views, features->height, features->width, grids, mode, threshold,
+                                          depth_points);
+    const cudaError_t e = run_fill(to_dev(*grid), pinv, *features, t_one, mode, workspace, ws, normalize, mean, rows,
+                                   row_stride, wsum, wtot, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
+}
+
+int cnrma_rma_fill(const cnrma_grid *grid, const float *pinv, const cnrma_features *features, int grids, float t_one,
+                   int mode, float threshold, int depth_points, const void *workspace, const cnrma_rma_result *result,
+                   int64_t rows_host, int normalize, const float *mean, float *rows, int64_t row_stride,
+                   int64_t capacity, void *stream) {
+    if (!rows || !result || rows_host < 0) return CNRMA_ERR_ARG;
+    if (!features) return CNRMA_ERR_ARG;
+    const int cols = features->channels + (normalize ? 3 : 4);
+    if (row_stride < cols) return CNRMA_ERR_ARG;
+    if (capacity < rows_host) return CNRMA_ERR_CAPACITY;
+    if (rows_host == 0) return CNRMA_OK;
+    const float *mean_ptr = mean ? mean : &result->mean;
+    return fill_common(grid, pinv, features, grids, t_one, mode, threshold, depth_points, workspace, normalize,
+                       mean_ptr, rows, row_stride, nullptr, nullptr, stream);
+}
+
+int cnrma_rma_scatter(const cnrma_grid *grid, const float *pinv, const cnrma_features *features, int grids,
+                      float t_one, int mode, float threshold, int depth_points, const void *workspace, float *wsum,
+                      float *wtot, void *stream) {
+    if (!wsum || !wtot) return CNRMA_ERR_ARG;
+    return fill_common(grid, pinv, features, grids, t_one, mode, threshold, depth_points, workspace, 0, nullptr,
+                       nullptr, 0, wsum, wtot, stream);
+}
+
+int cnrma_rma_expand(int views, int height, int width, int grids, float threshold, const void *workspace,
+                     float *weights, uint8_t *keep, void *stream) {
+    if (!workspace || views <= 0 || height <= 0 || width <= 0 || grids <= 0) return CNRMA_ERR_ARG;
+    const int d = device_ok();
+    if (d != CNRMA_OK) return d;
+    const RmaWorkspace ws = rma_workspace(views, height, width, grids, CNRMA_MARCH_NEUS, threshold, 0);
+    const cudaError_t e = run_expand(ws.rays, grids, workspace, ws, weights, keep, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
+}
+
+}  // extern "C"

@@ -1,0 +1,115 @@
+// Shared device helpers for libcnrma_b200 (sm_100a only; no CPU path).
+//
+// Numerics contract (DESIGN.md "Numerics"): the reference's fp32 torch ops are reproduced one rounding
+// at a time with explicit round-to-nearest intrinsics, so results do not depend on nvcc's contraction
+// choices; the library is additionally compiled with --fmad=false.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/cnrma_b200.h"
+
+namespace cnrma {
+
+constexpr int kWarp = 32;
+constexpr int kAggThreads = 256;            // 8 warps per CTA
+constexpr int kMaxViewsPerLaunch = 512;     // per-view device pointers travel in kernel params (4 KB of the 32 KB CUDA >= 12.1 allows)
+constexpr int kRayThreads = 256;            // rays per CTA in the march / fill kernels
+
+struct GridDev {
+    int nx, ny, nz;
+    float vs;
+    float ox, oy, oz;
+};
+
+static inline GridDev to_dev(const cnrma_grid &g) {
+    return GridDev{g.nx, g.ny, g.nz, g.voxel_size, g.origin[0], g.origin[1], g.origin[2]};
+}
+
+// torch.bmm([3|4]x4 @ 4xN) in fp32 == this FMA chain in k order (rm.py:51, :105-107).
+__device__ __forceinline__ float row_dot4(float p0, float p1, float p2, float p3, float x, float y, float z,
+                                          float w) {
+    float acc = __fmul_rn(p0, x);
+    acc = __fmaf_rn(p1, y, acc);
+    acc = __fmaf_rn(p2, z, acc);
+    acc = __fmaf_rn(p3, w, acc);
+    return acc;
+}
+
+// One voxel through one stride-scaled projection (rm.py:48-58).  P points at 12 floats with element
+// stride `ps` (shared memory, structure-of-arrays over views).  Returns true when the voxel is inside
+// the view frustum; px/py are the rounded pixel coordinates (exact integers as floats).
+__device__ __forceinline__ bool project_voxel(const float *P, int ps, float wx, float wy, float wz, int H, int W,
+                                              int &px, int &py) {
+    const float cx = row_dot4(P[0 * ps], P[1 * ps], P[2 * ps], P[3 * ps], wx, wy, wz, 1.0f);
+    const float cy = row_dot4(P[4 * ps], P[5 * ps], P[6 * ps], P[7 * ps], wx, wy, wz, 1.0f);
+    const float cz = row_dot4(P[8 * ps], P[9 * ps], P[10 * ps], P[11 * ps], wx, wy, wz, 1.0f);
+    const float rx = rintf(__fdiv_rn(cx, cz));  // Tensor.round() is half-to-even
+    const float ry = rintf(__fdiv_rn(cy, cz));
+    // The reference converts to int64 and compares; comparing the integer-valued floats is equivalent for
+    // every finite value, and NaN / +-inf (which x86 turns into INT64_MIN) fail the test either way.
+    const bool ok = (rx >= 0.0f) && (ry >= 0.0f) && (rx < (float)W) && (ry < (float)H) && (cz > 0.0f);
+    px = ok ? (int)rx : 0;
+    py = ok ? (int)ry : 0;
+    return ok;
+}
+
+// world = float(index) * voxel_size + origin: two roundings (rm.py:48).
+__device__ __forceinline__ float world_coord(int i, float vs, float o) { return __fadd_rn(__fmul_rn((float)i, vs), o); }
+
+// get_ray_parameter for one pixel (rm.py:71-111) given Pinv (16 floats, row major).
+__device__ __forceinline__ void ray_of_pixel(const float *__restrict__ Pinv, int u, int v, float o[3], float d[3]) {
+    const float fu = (float)u, fv = (float)v;
+    const float zu = __fmul_rn(fu, 0.0f), zv = __fmul_rn(fv, 0.0f);
+    float raw[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const float p0 = Pinv[4 * r + 0], p1 = Pinv[4 * r + 1], p2 = Pinv[4 * r + 2], p3 = Pinv[4 * r + 3];
+        o[r] = row_dot4(p0, p1, p2, p3, zu, zv, 0.0f, 1.0f);
+        raw[r] = __fsub_rn(row_dot4(p0, p1, p2, p3, fu, fv, 1.0f, 1.0f), o[r]);
+    }
+    // F.normalize: three separately rounded squares summed left to right, sqrt, clamp_min(1e-12), divide
+    float ss = __fadd_rn(__fmul_rn(raw[0], raw[0]), __fmul_rn(raw[1], raw[1]));
+    ss = __fadd_rn(ss, __fmul_rn(raw[2], raw[2]));
+    float nrm = __fsqrt_rn(ss);
+    nrm = (nrm < 1e-12f) ? 1e-12f : nrm;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) d[r] = __fdiv_rn(raw[r], nrm);
+}
+
+// ---- 16-byte feature vectors ---------------------------------------------------------------------
+template <typename T>
+struct Vec16;
+
+template <>
+struct Vec16<float> {
+    static constexpr int kElems = 4;
+    float v[4];
+    __device__ __forceinline__ static Vec16 load(const float *p) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+        Vec16 r;
+        r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+        return r;
+    }
+};
+
+template <>
+struct Vec16<__nv_bfloat16> {
+    static constexpr int kElems = 8;
+    float v[8];
+    __device__ __forceinline__ static Vec16 load(const __nv_bfloat16 *p) {
+        const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p));
+        Vec16 r;
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            r.v[2 * i + 0] = __uint_as_float(w[i] << 16);          // bf16 -> f32 is exact
+            r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+        return r;
+    }
+};
+
+}  // namespace cnrma

@@ -1,0 +1,37 @@
+// Internal launch interface between cnrma_abi.cu and the kernel translation units.
+#pragma once
+
+#include "cnrma_common.cuh"
+
+namespace cnrma {
+
+// Scratch layout of the ray-march path (byte offsets into the caller's workspace).
+struct RmaWorkspace {
+    int64_t rays;     // V*H*W
+    int64_t blocks;   // ceil(rays / kRayThreads)
+    int cap;          // (step, weight) records per ray
+    size_t off_counts, off_blk_rows, off_blk_wsum, off_blk_off, off_rec_w, off_rec_i, total;
+};
+
+// cnrma_stage_a.cu
+cudaError_t run_project_views(const GridDev &g, const float *proj, int64_t proj_stride, int V, float stride, int H,
+                              int W, int32_t *px, int32_t *py, uint8_t *valid, cudaStream_t stream);
+cudaError_t run_aggregate_views(const GridDev &g, const cnrma_features &f, int v0, int nv, const float *proj,
+                                int64_t proj_stride, float stride, uint32_t flags, float *volume, int64_t vsv,
+                                int64_t vsc, int32_t *count, uint8_t *valid, int max_chunk_vecs, cudaStream_t stream);
+cudaError_t run_to_channels_last(const void *src, int dtype, int C, int H, int W, int64_t sc, int64_t sy, int64_t sx,
+                                 void *dst, cudaStream_t stream);
+
+// cnrma_stage_b.cu
+RmaWorkspace rma_workspace(int views, int height, int width, int grids, int mode, float threshold, int depth_points);
+cudaError_t run_march(const GridDev &g, const float *pinv, int V, int H, int W, const float *tsdf, int N, float t_one,
+                      int mode, float thr, int depth_points, void *workspace, const RmaWorkspace &ws,
+                      cnrma_rma_result *result, cudaStream_t stream);
+cudaError_t run_fill(const GridDev &g, const float *pinv, const cnrma_features &f, float t_one, int mode,
+                     const void *workspace, const RmaWorkspace &ws, int normalize, const float *mean, float *rows,
+                     int64_t row_stride, float *wsum, float *wtot, cudaStream_t stream);
+cudaError_t run_ray_parameters(const float *pinv, int V, int H, int W, float *o, float *d, cudaStream_t stream);
+cudaError_t run_expand(int64_t rays, int N, const void *workspace, const RmaWorkspace &ws, float *weights,
+                       uint8_t *keep, cudaStream_t stream);
+
+}  // namespace cnrma

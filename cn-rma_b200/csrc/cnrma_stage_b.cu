@@ -1,0 +1,536 @@
+// Stage B: ray-marching aggregation -- per-pixel rays marched through the TSDF, NeuS opacity /
+// transmittance weights (or the depth-crossing variant), ordered compaction, feature copy and weight
+// normalisation (reference: rm.py:71-111, :260-307, :687-956).
+//
+// Three launches per scene (DESIGN.md "K_B"):
+//   march  one thread per ray; writes the ray's kept samples as (step, weight) records, its count, and a
+//          per-CTA row total and weight sum.  Exact early exits: transmittance below the threshold, and
+//          leaving the (convex) grid after having been inside it.
+//   scan   one CTA: exclusive scan of the per-CTA totals -> row offsets, M, sum(w), mean(w).
+//   fill   one CTA per 256 rays: per-ray offsets by warp scan, then each warp streams its rays' rows --
+//          the pixel's feature vector is read once into registers and written once per kept sample,
+//          scaled by w/mean, as coalesced row segments.
+#include "cnrma_internal.cuh"
+
+namespace cnrma {
+
+// ---- workspace layout ------------------------------------------------------------------------------
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int rma_record_capacity(int grids, int mode, float threshold, int depth_points) {
+    if (mode == CNRMA_MARCH_DEPTH) return depth_points > 0 ? 2 * depth_points : 1;
+    // kept NeuS weights are >= threshold and sum to at most 1 (+ rounding), so a ray keeps at most 1/threshold
+    if (threshold > 0.0f) {
+        const double k = 1.0 / (double)threshold + 2.0;
+        return k < (double)grids ? (int)k : grids;
+    }
+    return grids;
+}
+
+RmaWorkspace rma_workspace(int views, int height, int width, int grids, int mode, float threshold, int depth_points) {
+    RmaWorkspace w;
+    w.rays = (int64_t)views * height * width;
+    w.blocks = (w.rays + kRayThreads - 1) / kRayThreads;
+    w.cap = rma_record_capacity(grids, mode, threshold, depth_points);
+    size_t o = 0;
+    w.off_counts = o;   o = align256(o + sizeof(int32_t) * (size_t)w.rays);
+    w.off_blk_rows = o; o = align256(o + sizeof(int32_t) * (size_t)w.blocks);
+    w.off_blk_wsum = o; o = align256(o + sizeof(double) * (size_t)w.blocks);
+    w.off_blk_off = o;  o = align256(o + sizeof(int64_t) * (size_t)w.blocks);
+    w.off_rec_w = o;    o = align256(o + sizeof(float) * (size_t)w.rays * (size_t)w.cap);
+    w.off_rec_i = o;    o = align256(o + sizeof(float) * (size_t)w.rays * (size_t)w.cap);
+    w.total = o;
+    return w;
+}
+
+struct MarchParams {
+    GridDev g;
+    const float *pinv;   // [V][16]
+    const float *tsdf;
+    int V, H, W, N;
+    float t_one, thr;
+    int depth_points;
+    int cap;
+    int64_t rays;
+    int32_t *counts;
+    int32_t *blk_rows;
+    double *blk_wsum;
+    float *rec_w, *rec_i;
+    cnrma_rma_result *result;
+};
+
+// One sample of a ray (rm.py:729-733): position -> rounded voxel id; returns the flat id or -1 outside the grid.
+__device__ __forceinline__ int sample_voxel(const GridDev &g, const float o[3], const float d[3], float t) {
+    const float px = __fadd_rn(o[0], __fmul_rn(d[0], t));
+    const float py = __fadd_rn(o[1], __fmul_rn(d[1], t));
+    const float pz = __fadd_rn(o[2], __fmul_rn(d[2], t));
+    // ((places - origin) / voxel_size).round(): sub, true division, half-to-even (rm.py:730)
+    const float qx = rintf(__fdiv_rn(__fsub_rn(px, g.ox), g.vs));
+    const float qy = rintf(__fdiv_rn(__fsub_rn(py, g.oy), g.vs));
+    const float qz = rintf(__fdiv_rn(__fsub_rn(pz, g.oz), g.vs));
+    const bool inb = (qx >= 0.0f) && (qx < (float)g.nx) && (qy >= 0.0f) && (qy < (float)g.ny) && (qz >= 0.0f) &&
+                     (qz < (float)g.nz);
+    return inb ? (((int)qx * g.ny + (int)qy) * g.nz + (int)qz) : -1;
+}
+
+__device__ __forceinline__ float sigmoid_neg(float tv) {
+    // torch.sigmoid(-tsdf) = 1 / (1 + exp(tsdf)) (rm.py:757)
+    return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(tv)));
+}
+
+template <int BLOCK>
+__device__ __forceinline__ void block_totals(int kept, double wsum, int32_t *blk_rows, double *blk_wsum) {
+    __shared__ int s_rows[BLOCK / kWarp];
+    __shared__ double s_w[BLOCK / kWarp];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        kept += __shfl_down_sync(0xffffffffu, kept, o);
+        wsum += __shfl_down_sync(0xffffffffu, wsum, o);
+    }
+    if (lane == 0) {
+        s_rows[warp] = kept;
+        s_w[warp] = wsum;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int r = 0;
+        double w = 0.0;
+        for (int i = 0; i < BLOCK / kWarp; ++i) {
+            r += s_rows[i];
+            w += s_w[i];
+        }
+        blk_rows[blockIdx.x] = r;
+        blk_wsum[blockIdx.x] = w;
+    }
+}
+
+// NeuS march (rm.py:710-767).  Streaming form of
+//   s_i = sigmoid(-tsdf_i); alpha_i = max((s_i - s_{i+1}) / s_i, 0) with s_N := s_{N-1};
+//   T_i = prod_{j<i} (1 - alpha_j) (sequential product, like torch.cumprod on CPU); w_i = T_i * alpha_i;
+//   keep_i = in-bounds_i & (w_i >= thr).
+__global__ void __launch_bounds__(kRayThreads) march_neus_kernel(const __grid_constant__ MarchParams p) {
+    const int64_t ray = (int64_t)blockIdx.x * kRayThreads + threadIdx.x;
+    int kept = 0;
+    double wsum = 0.0;
+    if (ray < p.rays) {
+        const int hw = p.H * p.W;
+        const int view = (int)(ray / hw);
+        const int pix = (int)(ray % hw);
+        float o[3], d[3];
+        ray_of_pixel(p.pinv + 16 * view, pix % p.W, pix / p.W, o, d);
+
+        const float s_out = sigmoid_neg(1.0f);   // samples outside the grid read tsdf = 1.0 (rm.py:744)
+        float T = 1.0f;
+        float s_cur = 0.0f;
+        int vox_cur = -1;
+        bool entered = false;
+        int overflow = 0;
+        for (int i = 0; i <= p.N; ++i) {
+            float s_next;
+            int vox_next;
+            if (i < p.N) {
+                vox_next = sample_voxel(p.g, o, d, __fmul_rn((float)i, p.t_one));
+                if (i > 0 && vox_next == vox_cur) s_next = s_cur;   // same voxel -> same tsdf -> same sigmoid
+                else s_next = (vox_next >= 0) ? sigmoid_neg(__ldg(p.tsdf + vox_next)) : s_out;
+            } else {
+                vox_next = -1;
+                s_next = s_cur;   // last sample repeated (rm.py:758)
+            }
+            if (i > 0) {
+                float a = __fdiv_rn(__fsub_rn(s_cur, s_next), s_cur);
+                a = (a < 0.0f) ? 0.0f : a;   // clamp(min=0), NaN-propagating like torch
+                const float w = __fmul_rn(T, a);
+                if (vox_cur >= 0 && w >= p.thr) {
+                    if (kept < p.cap) {
+                        p.rec_w[(int64_t)kept * p.rays + ray] = w;
+                        p.rec_i[(int64_t)kept * p.rays + ray] = (float)(i - 1);
+                        wsum += (double)w;
+                        ++kept;
+                    } else {
+                        overflow = 1;
+                    }
+                }
+                T = __fmul_rn(T, __fsub_rn(1.0f, a));
+                // exact early exits: (a) every later weight is <= T < thr; (b) the grid is convex and the
+                // rounded sample ids are monotone along the ray, so once left it is never re-entered and
+                // samples outside are never kept.
+                if (p.thr > 0.0f && T < p.thr) break;
+                if (entered && vox_next < 0) break;
+            }
+            entered = entered || (vox_next >= 0);
+            s_cur = s_next;
+            vox_cur = vox_next;
+        }
+        p.counts[ray] = kept;
+        if (overflow) atomicAdd(&p.result->overflow, 1);
+    }
+    block_totals<kRayThreads>(kept, wsum, p.blk_rows, p.blk_wsum);
+}
+
+// Depth-crossing march (rm.py:826-911): first step i with tsdf_i * tsdf_{i+1} <= 0, then either the 2k
+// neighbouring steps with triangular weights (k = depth_points > 0) or the half-step point (k == 0).
+__global__ void __launch_bounds__(kRayThreads) march_depth_kernel(const __grid_constant__ MarchParams p) {
+    const int64_t ray = (int64_t)blockIdx.x * kRayThreads + threadIdx.x;
+    int kept = 0;
+    double wsum = 0.0;
+    if (ray < p.rays) {
+        const int hw = p.H * p.W;
+        const int view = (int)(ray / hw);
+        const int pix = (int)(ray % hw);
+        float o[3], d[3];
+        ray_of_pixel(p.pinv + 16 * view, pix % p.W, pix / p.W, o, d);
+        int best = -1;
+        float tv_cur = 1.0f;
+        int vox_cur = -1;
+        for (int i = 0; i < p.N; ++i) {
+            const int vox = sample_voxel(p.g, o, d, __fmul_rn((float)i, p.t_one));
+            const float tv = (i > 0 && vox == vox_cur) ? tv_cur : ((vox >= 0) ? __ldg(p.tsdf + vox) : 1.0f);
+            if (i > 0 && __fmul_rn(tv_cur, tv) <= 0.0f) {
+                best = i - 1;
+                break;
+            }
+            tv_cur = tv;
+            vox_cur = vox;
+        }
+        if (best >= 0) {
+            const int k = p.depth_points;
+            if (k > 0) {
+                for (int j = 0; j < 2 * k; ++j) {
+                    const int idx = best + j - k + 1;
+                    const int tri = (j < k) ? (j + 1) : (2 * k - j);
+                    const float w = __fdiv_rn((float)tri, (float)k);   // multi_weight.float() / select_grids
+                    if (idx < 0 || idx >= p.N || !(w > 0.0f)) continue;
+                    p.rec_w[(int64_t)kept * p.rays + ray] = w;
+                    p.rec_i[(int64_t)kept * p.rays + ray] = (float)idx;
+                    wsum += (double)w;
+                    ++kept;
+                }
+            } else {
+                p.rec_w[ray] = 1.0f;
+                p.rec_i[ray] = __fadd_rn((float)best, 0.5f);
+                wsum = 1.0;
+                kept = 1;
+            }
+        }
+        p.counts[ray] = kept;
+    }
+    block_totals<kRayThreads>(kept, wsum, p.blk_rows, p.blk_wsum);
+}
+
+// Exclusive scan of the per-CTA row totals; fixed-shape reduction of the weight sums (deterministic).
+constexpr int kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads) scan_blocks_kernel(const int32_t *__restrict__ blk_rows,
+                                                                   const double *__restrict__ blk_wsum,
+                                                                   int64_t *__restrict__ blk_off, int64_t blocks,
+                                                                   cnrma_rma_result *result) {
+    __shared__ int64_t s_rows[kScanThreads];
+    __shared__ double s_w[kScanThreads];
+    const int t = threadIdx.x;
+    const int64_t per = (blocks + kScanThreads - 1) / kScanThreads;
+    const int64_t lo = (int64_t)t * per;
+    const int64_t hi = (lo + per < blocks) ? lo + per : blocks;
+    int64_t rows = 0;
+    double w = 0.0;
+    for (int64_t i = lo; i < hi; ++i) {
+        rows += blk_rows[i];
+        w += blk_wsum[i];
+    }
+    s_rows[t] = rows;
+    s_w[t] = w;
+    __syncthreads();
+    // Hillis-Steele inclusive scan of the strip totals (rows) and a pairwise tree for the weights
+    for (int o = 1; o < kScanThreads; o <<= 1) {
+        const int64_t add = (t >= o) ? s_rows[t - o] : 0;
+        __syncthreads();
+        s_rows[t] += add;
+        __syncthreads();
+    }
+    for (int o = kScanThreads / 2; o > 0; o >>= 1) {
+        if (t < o) s_w[t] += s_w[t + o];
+        __syncthreads();
+    }
+    int64_t run = s_rows[t] - rows;   // exclusive prefix of this strip
+    for (int64_t i = lo; i < hi; ++i) {
+        blk_off[i] = run;
+        run += blk_rows[i];
+    }
+    if (t == kScanThreads - 1) {
+        result->rows = s_rows[t];
+        result->weight_sum = s_w[0];
+        result->mean = (s_rows[t] > 0) ? (float)(s_w[0] / (double)s_rows[t]) : 0.0f;
+    }
+}
+
+// ---- fill ------------------------------------------------------------------------------------------
+struct FillParams {
+    GridDev g;
+    const float *pinv;
+    int V, C, H, W;
+    int64_t stride_y, stride_x;
+    float t_one;
+    int mode;          // cnrma_march_mode: selects how a record's step becomes a position
+    int normalize;     // 1: [x,y,z, feat*w/mean]   0: [x,y,z,w, feat]
+    int64_t rays;
+    const int32_t *counts;
+    const int64_t *blk_off;
+    const float *rec_w, *rec_i;
+    const float *mean;
+    float *rows;
+    int64_t row_stride;
+    float *wsum, *wtot;   // scatter variant
+    const void *views[kMaxViewsPerLaunch];
+    int view_base;        // first view of this launch
+};
+
+__device__ __forceinline__ void record_position(const FillParams &p, const float o[3], const float d[3], float fi,
+                                                float pos[3]) {
+    if (p.mode == CNRMA_MARCH_NEUS) {
+        const float t = __fmul_rn(fi, p.t_one);   // places = o + d * (i * t_one), rm.py:715,729
+#pragma unroll
+        for (int r = 0; r < 3; ++r) pos[r] = __fadd_rn(o[r], __fmul_rn(d[r], t));
+    } else {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)   // selected_places = o + (d * index) * t_one, rm.py:901,910
+            pos[r] = __fadd_rn(o[r], __fmul_rn(__fmul_rn(d[r], fi), p.t_one));
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ float load_feat(const T *p);
+template <>
+__device__ __forceinline__ float load_feat<float>(const float *p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float load_feat<__nv_bfloat16>(const __nv_bfloat16 *p) {
+    return __uint_as_float(((uint32_t)__ldg(reinterpret_cast<const unsigned short *>(p))) << 16);
+}
+
+constexpr int kFillRegs = 8;   // channels per lane per pass in the fill kernel (8*32 = 256 channels)
+
+// SCATTER = false: write rows.  SCATTER = true: atomically add w*feat into wsum[voxel] and w into wtot[voxel].
+template <typename T, bool SCATTER>
+__global__ void __launch_bounds__(kRayThreads) fill_rows_kernel(const __grid_constant__ FillParams p) {
+    __shared__ int s_warp_rows[kRayThreads / kWarp];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int hw = p.H * p.W;
+    // this launch covers views [view_base, view_base + V): rays are numbered globally
+    const int64_t ray0 = (int64_t)p.view_base * hw + (int64_t)blockIdx.x * kRayThreads;
+    const int64_t my_ray = ray0 + threadIdx.x;
+    const int64_t ray_end = (int64_t)(p.view_base + p.V) * hw;
+    const int my_cnt = (my_ray < ray_end && my_ray < p.rays) ? p.counts[my_ray] : 0;
+    // exclusive offsets: warp scan + per-warp totals
+    int incl = my_cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) s_warp_rows[warp] = incl;
+    __syncthreads();
+    int64_t base = p.blk_off[ray0 / kRayThreads];
+    for (int i = 0; i < warp; ++i) base += s_warp_rows[i];
+    const int64_t my_off = base + (incl - my_cnt);
+    const float mean = (p.normalize && !SCATTER) ? __ldg(p.mean) : 1.0f;
+    const int col0 = SCATTER ? 0 : (p.normalize ? 3 : 4);
+
+    for (int r = 0; r < 32; ++r) {
+        const int cnt = __shfl_sync(0xffffffffu, my_cnt, r);
+        if (cnt == 0) continue;
+        const int64_t off = __shfl_sync(0xffffffffu, my_off, r);
+        const int64_t ray = ray0 + warp * 32 + r;
+        const int view = (int)(ray / hw);
+        const int pix = (int)(ray % hw);
+        const int u = pix % p.W, v = pix / p.W;
+        float o[3], d[3];
+        ray_of_pixel(p.pinv + 16 * view, u, v, o, d);
+        const T *feat = static_cast<const T *>(p.views[view - p.view_base]) + (int64_t)v * p.stride_y + (int64_t)u * p.stride_x;
+        // records of this ray: lane k holds record k (cap <= 32 is the common case; loop otherwise)
+        for (int cbase = 0; cbase < p.C; cbase += 32 * kFillRegs) {
+            float f[kFillRegs];
+#pragma unroll
+            for (int j = 0; j < kFillRegs; ++j) {
+                const int c = cbase + j * 32 + lane;
+                f[j] = (c < p.C) ? load_feat<T>(feat + c) : 0.0f;
+            }
+            for (int k = 0; k < cnt; ++k) {
+                const float w = __ldg(p.rec_w + (int64_t)k * p.rays + ray);
+                const float fi = __ldg(p.rec_i + (int64_t)k * p.rays + ray);
+                float pos[3];
+                record_position(p, o, d, fi, pos);
+                if (!SCATTER) {
+                    float *row = p.rows + (off + k) * p.row_stride;
+                    const float wn = p.normalize ? __fdiv_rn(w, mean) : 1.0f;   // weights / mean(weights), rm.py:303
+                    if (cbase == 0) {
+                        if (lane < 3) row[lane] = pos[lane];
+                        if (lane == 3 && !p.normalize) row[3] = w;
+                    }
+#pragma unroll
+                    for (int j = 0; j < kFillRegs; ++j) {
+                        const int c = cbase + j * 32 + lane;
+                        if (c < p.C) __stcs(row + col0 + c, p.normalize ? __fmul_rn(f[j], wn) : f[j]);
+                    }
+                } else {
+                    const float qx = rintf(__fdiv_rn(__fsub_rn(pos[0], p.g.ox), p.g.vs));
+                    const float qy = rintf(__fdiv_rn(__fsub_rn(pos[1], p.g.oy), p.g.vs));
+                    const float qz = rintf(__fdiv_rn(__fsub_rn(pos[2], p.g.oz), p.g.vs));
+                    const bool inb = (qx >= 0.0f) && (qx < (float)p.g.nx) && (qy >= 0.0f) && (qy < (float)p.g.ny) &&
+                                     (qz >= 0.0f) && (qz < (float)p.g.nz);
+                    if (!inb) continue;
+                    const int64_t vox = ((int64_t)(int)qx * p.g.ny + (int)qy) * p.g.nz + (int)qz;
+                    if (cbase == 0 && lane == 0) atomicAdd(p.wtot + vox, w);
+#pragma unroll
+                    for (int j = 0; j < kFillRegs; ++j) {
+                        const int c = cbase + j * 32 + lane;
+                        if (c < p.C) atomicAdd(p.wsum + vox * p.C + c, __fmul_rn(w, f[j]));
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Dense view of the records for parity tests: weights * valid_final and valid_final (rm.py:765-767).
+__global__ void __launch_bounds__(256) expand_records_kernel(int64_t rays, int N, const int32_t *__restrict__ counts,
+                                                             const float *__restrict__ rec_w,
+                                                             const float *__restrict__ rec_i,
+                                                             float *__restrict__ weights, uint8_t *__restrict__ keep) {
+    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= rays) return;
+    const int cnt = counts[ray];
+    for (int k = 0; k < cnt; ++k) {
+        const int i = (int)rec_i[(int64_t)k * rays + ray];
+        if (weights) weights[ray * N + i] = rec_w[(int64_t)k * rays + ray];
+        if (keep) keep[ray * N + i] = 1;
+    }
+}
+
+// get_ray_parameter as tensors (rm.py:71-111): o, d [V,3,H*W].
+__global__ void __launch_bounds__(256) ray_parameters_kernel(const float *__restrict__ pinv, int V, int H, int W,
+                                                             float *__restrict__ o_out, float *__restrict__ d_out) {
+    const int hw = H * W;
+    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= (int64_t)V * hw) return;
+    const int view = (int)(ray / hw), pix = (int)(ray % hw);
+    float o[3], d[3];
+    ray_of_pixel(pinv + 16 * view, pix % W, pix / W, o, d);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        o_out[((int64_t)view * 3 + r) * hw + pix] = o[r];
+        d_out[((int64_t)view * 3 + r) * hw + pix] = d[r];
+    }
+}
+
+cudaError_t run_ray_parameters(const float *pinv, int V, int H, int W, float *o, float *d, cudaStream_t stream) {
+    const int64_t rays = (int64_t)V * H * W;
+    ray_parameters_kernel<<<(unsigned)((rays + 255) / 256), 256, 0, stream>>>(pinv, V, H, W, o, d);
+    return cudaGetLastError();
+}
+
+// ---- host-side launchers -----------------------------------------------------------------------------
+
+cudaError_t run_march(const GridDev &g, const float *pinv, int V, int H, int W, const float *tsdf, int N, float t_one,
+                      int mode, float thr, int depth_points, void *workspace, const RmaWorkspace &ws,
+                      cnrma_rma_result *result, cudaStream_t stream) {
+    unsigned char *base = static_cast<unsigned char *>(workspace);
+    MarchParams p;
+    p.g = g;
+    p.pinv = pinv;
+    p.tsdf = tsdf;
+    p.V = V; p.H = H; p.W = W; p.N = N;
+    p.t_one = t_one;
+    p.thr = thr;
+    p.depth_points = depth_points;
+    p.cap = ws.cap;
+    p.rays = ws.rays;
+    p.counts = reinterpret_cast<int32_t *>(base + ws.off_counts);
+    p.blk_rows = reinterpret_cast<int32_t *>(base + ws.off_blk_rows);
+    p.blk_wsum = reinterpret_cast<double *>(base + ws.off_blk_wsum);
+    p.rec_w = reinterpret_cast<float *>(base + ws.off_rec_w);
+    p.rec_i = reinterpret_cast<float *>(base + ws.off_rec_i);
+    p.result = result;
+    cudaError_t err = cudaMemsetAsync(result, 0, sizeof(cnrma_rma_result), stream);
+    if (err != cudaSuccess) return err;
+    if (mode == CNRMA_MARCH_DEPTH)
+        march_depth_kernel<<<(unsigned)ws.blocks, kRayThreads, 0, stream>>>(p);
+    else
+        march_neus_kernel<<<(unsigned)ws.blocks, kRayThreads, 0, stream>>>(p);
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    scan_blocks_kernel<<<1, kScanThreads, 0, stream>>>(p.blk_rows, p.blk_wsum,
+                                                       reinterpret_cast<int64_t *>(base + ws.off_blk_off), ws.blocks,
+                                                       result);
+    return cudaGetLastError();
+}
+
+template <bool SCATTER>
+static cudaError_t launch_fill(FillParams &p, int dtype, const void *const *view_ptrs_host, int V_total,
+                               cudaStream_t stream) {
+    const int hw = p.H * p.W;
+    // One launch normally.  Beyond kMaxViewsPerLaunch views (pointer table in kernel params) the views go
+    // out in groups whose ray count is a whole number of CTAs, so that the per-CTA row offsets written by
+    // the march kernel line up with this kernel's CTAs.
+    int group = V_total;
+    if (V_total > kMaxViewsPerLaunch) {
+        group = kMaxViewsPerLaunch;
+        while (group > 0 && ((int64_t)group * hw) % kRayThreads != 0) --group;
+        if (group == 0) return cudaErrorInvalidValue;
+    }
+    for (int v0 = 0; v0 < V_total; v0 += group) {
+        const int nv = (V_total - v0 < group) ? (V_total - v0) : group;
+        p.view_base = v0;
+        p.V = nv;
+        for (int i = 0; i < nv; ++i) p.views[i] = view_ptrs_host[v0 + i];
+        const int64_t rays = (int64_t)nv * hw;
+        const unsigned blocks = (unsigned)((rays + kRayThreads - 1) / kRayThreads);
+        if (dtype == CNRMA_BF16)
+            fill_rows_kernel<__nv_bfloat16, SCATTER><<<blocks, kRayThreads, 0, stream>>>(p);
+        else
+            fill_rows_kernel<float, SCATTER><<<blocks, kRayThreads, 0, stream>>>(p);
+        const cudaError_t err = cudaGetLastError();
+        if (err != cudaSuccess) return err;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t run_fill(const GridDev &g, const float *pinv, const cnrma_features &f, float t_one, int mode,
+                     const void *workspace, const RmaWorkspace &ws, int normalize, const float *mean, float *rows,
+                     int64_t row_stride, float *wsum, float *wtot, cudaStream_t stream) {
+    const unsigned char *base = static_cast<const unsigned char *>(workspace);
+    FillParams p;
+    p.g = g;
+    p.pinv = pinv;
+    p.V = f.views; p.C = f.channels; p.H = f.height; p.W = f.width;
+    p.stride_y = f.stride_y; p.stride_x = f.stride_x;
+    p.t_one = t_one;
+    p.mode = mode;
+    p.normalize = normalize;
+    p.rays = ws.rays;
+    p.counts = reinterpret_cast<const int32_t *>(base + ws.off_counts);
+    p.blk_off = reinterpret_cast<const int64_t *>(base + ws.off_blk_off);
+    p.rec_w = reinterpret_cast<const float *>(base + ws.off_rec_w);
+    p.rec_i = reinterpret_cast<const float *>(base + ws.off_rec_i);
+    p.mean = mean;
+    p.rows = rows;
+    p.row_stride = row_stride;
+    p.wsum = wsum;
+    p.wtot = wtot;
+    p.view_base = 0;
+    if (wsum != nullptr) return launch_fill<true>(p, f.dtype, f.view_ptrs_host, f.views, stream);
+    return launch_fill<false>(p, f.dtype, f.view_ptrs_host, f.views, stream);
+}
+
+cudaError_t run_expand(int64_t rays, int N, const void *workspace, const RmaWorkspace &ws, float *weights,
+                       uint8_t *keep, cudaStream_t stream) {
+    const unsigned char *base = static_cast<const unsigned char *>(workspace);
+    cudaError_t err = cudaSuccess;
+    if (weights) err = cudaMemsetAsync(weights, 0, sizeof(float) * (size_t)rays * N, stream);
+    if (err == cudaSuccess && keep) err = cudaMemsetAsync(keep, 0, (size_t)rays * N, stream);
+    if (err != cudaSuccess) return err;
+    expand_records_kernel<<<(unsigned)((rays + 255) / 256), 256, 0, stream>>>(
+        rays, N, reinterpret_cast<const int32_t *>(base + ws.off_counts),
+        reinterpret_cast<const float *>(base + ws.off_rec_w), reinterpret_cast<const float *>(base + ws.off_rec_i),
+        weights, keep);
+    return cudaGetLastError();
+}
+
+}  // namespace cnrma

@@ -1,0 +1,419 @@
+"""Functional host API: the reference's hot-path functions, same names and argument order, backed by the
+sm_100a kernels in libcnrma_b200.so.  ("rm.py" = projects/mvsdetection/models/ray_marching.py.)
+
+    backproject(voxel_dim, voxel_size, origin, projection, features)            rm.py:21
+    get_ray_parameter(projection, features)                                      rm.py:71
+plus the fused entry points the stateful mirror (module.py) is built on:
+    aggregate_views(...)   = V x aggregate_2d_features + clear_3d_features      rm.py:220-257
+    rma_points(...)        = aggregate_2d_features_ray_marching                  rm.py:260-307
+    ray_projection(...)    = ray_projection_neus / _depth for one view           rm.py:687 / :809
+    dense_rma(...)         = derived voxel-form of the RMA lift
+
+PyTorch is used for device memory, streams and the 4x4 LAPACK inverse the reference itself calls
+(rm.py:100); every other step runs in the CUDA library.  There is no CPU or eager fallback: tensors must
+live on a CUDA device and the library must be built.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import CnrmaError
+
+_DTYPES = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _origin3(origin):
+    if isinstance(origin, torch.Tensor):
+        return [float(v) for v in origin.detach().reshape(-1).to("cpu", torch.float32)]
+    return [float(v) for v in origin]
+
+
+def _as_view_list(features):
+    """[V,B,C,H,W] tensor or sequence of V [B,C,H,W] tensors -> list of V tensors."""
+    if isinstance(features, torch.Tensor):
+        if features.dim() != 5:
+            raise ValueError("features must be [V,B,C,H,W] or a sequence of [B,C,H,W]")
+        return [features[v] for v in range(features.shape[0])]
+    views = list(features)
+    if not views or any(f.dim() != 4 for f in views):
+        raise ValueError("features must be [V,B,C,H,W] or a sequence of [B,C,H,W]")
+    return views
+
+
+class _FeatureStack:
+    """Per-batch-element cnrma_features descriptors for a list of per-view [B,C,H,W] tensors.
+
+    Keeps the tensors (and any channels-last copies) alive for as long as the descriptor is used."""
+
+    def __init__(self, views, need_vector_layout):
+        f0 = views[0]
+        if not f0.is_cuda:
+            raise CnrmaError("features must be CUDA tensors: this path has no CPU implementation")
+        if f0.dtype not in _DTYPES:
+            raise CnrmaError(f"unsupported feature dtype {f0.dtype} (float32 or bfloat16)")
+        self.device = f0.device
+        self.dtype = f0.dtype
+        self.V = len(views)
+        self.B, self.C, self.H, self.W = f0.shape
+        for f in views:
+            if f.shape != f0.shape or f.dtype != f0.dtype or f.device != f0.device:
+                raise ValueError("all views must share shape, dtype and device")
+        self.views = [f.detach() for f in views]
+        e = 8 if self.dtype == torch.bfloat16 else 4
+        ok = self.C % e == 0 or not need_vector_layout
+        if not ok:
+            raise CnrmaError(f"channels must be a multiple of {e} for {self.dtype}")
+        strides = {f.stride()[1:] for f in self.views}
+        sc, sy, sx = next(iter(strides))
+        aligned = all(f[b].data_ptr() % 16 == 0 for f in self.views for b in range(self.B))
+        cl = len(strides) == 1 and sc == 1 and (not need_vector_layout or (sx % e == 0 and sy % e == 0 and aligned))
+        if not cl:
+            self.views = self._to_channels_last()
+        self.sc, self.sy, self.sx = self.views[0].stride()[1:]
+        self.converted = not cl
+
+    def _to_channels_last(self):
+        lib = _lib.load()
+        out = torch.empty((self.V, self.B, self.H, self.W, self.C), dtype=self.dtype, device=self.device)
+        for b in range(self.B):
+            for v, f in enumerate(self.views):   # one launch per map: strides may differ between views
+                ptrs = (C.c_void_p * 1)(f[b].data_ptr())
+                sc, sy, sx = f.stride()[1:]
+                desc = _lib.Features(1, self.C, self.H, self.W, _DTYPES[self.dtype], sc, sy, sx,
+                                     C.cast(ptrs, C.POINTER(C.c_void_p)))
+                _lib.check(lib.cnrma_to_channels_last(C.byref(desc), C.c_void_p(out[v, b].data_ptr()),
+                                                      _stream(self.device)), "cnrma_to_channels_last")
+        return [out[v].permute(0, 3, 1, 2) for v in range(self.V)]
+
+    def descriptor(self, b, v0=0, nv=None):
+        nv = self.V - v0 if nv is None else nv
+        ptrs = (C.c_void_p * nv)(*[self.views[v][b].data_ptr() for v in range(v0, v0 + nv)])
+        desc = _lib.Features(nv, self.C, self.H, self.W, _DTYPES[self.dtype], self.sc, self.sy, self.sx,
+                             C.cast(ptrs, C.POINTER(C.c_void_p)))
+        desc._keepalive = ptrs
+        return desc
+
+
+def _projections_device(projections, device):
+    """[V,B,3,4] (tensor or sequence of [B,3,4]) -> contiguous fp32 CUDA tensor."""
+    if not isinstance(projections, torch.Tensor):
+        projections = torch.stack(list(projections), dim=0)
+    if projections.dim() != 4 or projections.shape[-2:] != (3, 4):
+        raise ValueError("projections must be [V,B,3,4]")
+    return projections.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------
+# Stage A
+# ----------------------------------------------------------------------------------------------------
+
+def project_views(projections, voxel_dim, voxel_size, origin, stride, height, width, device=None):
+    """Index / mask part of backproject (rm.py:47-58) for all views.
+
+    projections [V,B,3,4] un-scaled -> (px, py int32 [V,B,nvox], valid bool [V,B,nvox]); bit-exact."""
+    lib = _lib.load()
+    device = torch.device(device) if device is not None else projections.device
+    P = _projections_device(projections, device)
+    V, B = P.shape[:2]
+    nvox = int(voxel_dim[0]) * int(voxel_dim[1]) * int(voxel_dim[2])
+    grid = _lib.make_grid(voxel_dim, voxel_size, _origin3(origin))
+    px = torch.empty((B, V, nvox), dtype=torch.int32, device=device)
+    py = torch.empty_like(px)
+    valid = torch.empty((B, V, nvox), dtype=torch.bool, device=device)
+    with torch.cuda.device(device):
+        for b in range(B):
+            _lib.check(lib.cnrma_project_views(C.byref(grid), C.c_void_p(P[0, b].data_ptr()), B * 12, V,
+                                               float(stride), int(height), int(width), C.c_void_p(px[b].data_ptr()),
+                                               C.c_void_p(py[b].data_ptr()), C.c_void_p(valid[b].data_ptr()),
+                                               _stream(device)), "cnrma_project_views")
+    return px.transpose(0, 1), py.transpose(0, 1), valid.transpose(0, 1)
+
+
+def aggregate_views(projections, features, voxel_dim, voxel_size, origin, stride, mean=True, out=None,
+                    accumulate=None, count_f32=False):
+    """Fused Stage A: V x aggregate_2d_features (+ clear_3d_features when mean=True), rm.py:220-257.
+
+    projections [V,B,3,4] un-scaled; features [V,B,C,H,W] or a sequence of [B,C,H,W].
+    Returns (volume [B,C,nx,ny,nz] fp32, count [B,1,nx,ny,nz] int32, valid [B,1,nx,ny,nz] bool).
+    `volume` is a channels_last_3d view of a [B,nx,ny,nz,C] buffer (logical NCDHW like the reference).
+    `out=(volume, count, valid)` supplies the buffers; with `accumulate` (default when `out` is given) the
+    new views are added to the un-averaged sums / counts already there (rm.py:243-244 semantics) and
+    `mean` finishes them.  `count_f32` stores the counts as float32 (exact below 2**24) so sums and counts
+    can share one fp32 all-reduce buffer (distributed.py)."""
+    lib = _lib.load()
+    fs = _FeatureStack(_as_view_list(features), need_vector_layout=True)
+    device = fs.device
+    P = _projections_device(projections, device)
+    if P.shape[0] != fs.V or P.shape[1] != fs.B:
+        raise ValueError("projections / features disagree on views or batch")
+    nx, ny, nz = (int(v) for v in voxel_dim)
+    grid = _lib.make_grid(voxel_dim, voxel_size, _origin3(origin))
+    flags = (_lib.AGG_MEAN if mean else 0) | (_lib.AGG_COUNT_F32 if count_f32 else 0)
+    if out is None:
+        buf = torch.empty((fs.B, nx, ny, nz, fs.C), dtype=torch.float32, device=device)
+        count = torch.empty((fs.B, 1, nx, ny, nz), dtype=torch.float32 if count_f32 else torch.int32, device=device)
+        valid = torch.empty((fs.B, 1, nx, ny, nz), dtype=torch.bool, device=device)
+        volume = buf.permute(0, 4, 1, 2, 3)
+    else:
+        volume, count, valid = out
+        if accumulate is None or accumulate:
+            flags |= _lib.AGG_ACCUMULATE
+        _check_out(volume, count, fs.B, fs.C, nx, ny, nz, count_f32)
+    with torch.cuda.device(device):
+        for b in range(fs.B):
+            desc = fs.descriptor(b)
+            vb = volume[b]
+            _lib.check(lib.cnrma_aggregate_views(C.byref(grid), C.byref(desc), C.c_void_p(P[0, b].data_ptr()),
+                                                 fs.B * 12, float(stride), flags, C.c_void_p(vb.data_ptr()),
+                                                 vb.stride(3), vb.stride(0), C.c_void_p(count[b].data_ptr()),
+                                                 C.c_void_p(valid[b].data_ptr()) if valid is not None else None,
+                                                 _stream(device)), "cnrma_aggregate_views")
+    return volume, count, valid
+
+
+def _check_out(volume, count, B, Cc, nx, ny, nz, count_f32):
+    if tuple(volume.shape) != (B, Cc, nx, ny, nz) or volume.dtype != torch.float32 or not volume.is_cuda:
+        raise ValueError("out volume has the wrong shape, dtype or device")
+    if count.dtype != (torch.float32 if count_f32 else torch.int32) or count.numel() != B * nx * ny * nz \
+            or not count.is_contiguous():
+        raise ValueError("out count has the wrong shape or dtype")
+
+
+def finalize_views(volume, count, valid=None, count_f32=False):
+    """clear_3d_features (rm.py:247-257) on sums / counts produced elsewhere -- e.g. after the all-reduce of
+    view-sharded partial results: volume <- volume / count in place, 0 where count == 0."""
+    lib = _lib.load()
+    B, Cc, nx, ny, nz = volume.shape
+    _check_out(volume, count, B, Cc, nx, ny, nz, count_f32)
+    device = volume.device
+    grid = _lib.make_grid((nx, ny, nz), 1.0, (0.0, 0.0, 0.0))
+    flags = _lib.AGG_ACCUMULATE | _lib.AGG_MEAN | (_lib.AGG_COUNT_F32 if count_f32 else 0)
+    desc = _lib.Features(0, Cc, 1, 1, _lib.F32, 1, Cc, Cc, None)
+    with torch.cuda.device(device):
+        for b in range(B):
+            vb = volume[b]
+            _lib.check(lib.cnrma_aggregate_views(C.byref(grid), C.byref(desc), None, 12, 1.0, flags,
+                                                 C.c_void_p(vb.data_ptr()), vb.stride(3), vb.stride(0),
+                                                 C.c_void_p(count[b].data_ptr()),
+                                                 C.c_void_p(valid[b].data_ptr()) if valid is not None else None,
+                                                 _stream(device)), "cnrma_aggregate_views(finalise)")
+    return volume
+
+
+def backproject(voxel_dim, voxel_size, origin, projection, features):
+    """Drop-in for rm.py:21-69.  projection [B,3,4] ALREADY divided by the stride (as the reference's caller
+    does, rm.py:238-239), features [B,C,H,W] -> (volume [B,C,nx,ny,nz], valid [B,1,nx,ny,nz] bool)."""
+    volume, _count, valid = aggregate_views(projection.unsqueeze(0), features.unsqueeze(0), voxel_dim, voxel_size,
+                                            origin, 1.0, mean=False)
+    return volume, valid
+
+
+# ----------------------------------------------------------------------------------------------------
+# Stage B
+# ----------------------------------------------------------------------------------------------------
+
+def invert_projections(projections_scaled):
+    """rm.py:96-102: inverse of [P; 0 0 0 1] per view, with the reference's own call (torch.inverse on one
+    4x4 fp32 matrix) on the host, so the ray parameters are bit-identical to the CPU reference.
+    projections_scaled [V,3,4] (any device) -> [V,4,4] CPU fp32."""
+    P = projections_scaled.detach().to("cpu", torch.float32)
+    last = torch.tensor([[0.0, 0.0, 0.0, 1.0]])
+    return torch.stack([torch.inverse(torch.cat((P[v], last), dim=0)) for v in range(P.shape[0])], dim=0)
+
+
+def scale_projections(projections, stride):
+    """rm.py:238-239 / :275-276 on the host copy: rows 0-1 divided by the backbone stride."""
+    P = projections.detach().to("cpu", torch.float32).clone()
+    P[..., :2, :] = P[..., :2, :] / stride
+    return P
+
+
+def get_ray_parameter(projection, features):
+    """Drop-in for rm.py:71-111.  projection [B,3,4] (already stride-scaled), features [B,C,H,W] ->
+    (o, d) each [B,3,H*W]."""
+    lib = _lib.load()
+    if not features.is_cuda:
+        raise CnrmaError("features must be a CUDA tensor")
+    device = features.device
+    B, _c, H, W = features.shape
+    pinv = invert_projections(projection).to(device)
+    o = torch.empty((B, 3, H * W), dtype=torch.float32, device=device)
+    d = torch.empty_like(o)
+    with torch.cuda.device(device):
+        _lib.check(lib.cnrma_ray_parameters(C.c_void_p(pinv.data_ptr()), B, H, W, C.c_void_p(o.data_ptr()),
+                                            C.c_void_p(d.data_ptr()), _stream(device)), "cnrma_ray_parameters")
+    return o, d
+
+
+class _March:
+    """State of one marched batch element: workspace, result block, and what fill/scatter need."""
+    pass
+
+
+def _march(fs, b, P_scaled_b, tsdf_b, grid, voxel_dim, voxel_size, grids, mode, threshold, depth_points):
+    lib = _lib.load()
+    device = fs.device
+    m = _March()
+    m.mode = _lib.MARCH_NEUS if mode == "neus" else _lib.MARCH_DEPTH
+    m.threshold = float(threshold if threshold is not None else 0.0)
+    m.depth_points = int(depth_points if depth_points is not None else 0)
+    m.grids = int(grids)
+    m.pinv = invert_projections(P_scaled_b).to(device)
+    m.t_one = lib.cnrma_t_one(C.byref(grid), float(voxel_size), m.grids)
+    nbytes = C.c_size_t(0)
+    _lib.check(lib.cnrma_rma_workspace_bytes(fs.V, fs.H, fs.W, m.grids, m.mode, m.threshold, m.depth_points,
+                                             C.byref(nbytes)), "cnrma_rma_workspace_bytes")
+    m.workspace = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
+    m.result = torch.empty(C.sizeof(_lib.RmaResult), dtype=torch.uint8, device=device)
+    tsdf_b = tsdf_b.detach().to(device=device, dtype=torch.float32).contiguous()
+    if tuple(tsdf_b.shape) != tuple(int(v) for v in voxel_dim):
+        raise ValueError("tsdf must be [B,1,nx,ny,nz]")
+    m.tsdf = tsdf_b
+    _lib.check(lib.cnrma_rma_march(C.byref(grid), C.c_void_p(m.pinv.data_ptr()), fs.V, fs.H, fs.W,
+                                   C.c_void_p(tsdf_b.data_ptr()), m.grids, m.t_one, m.mode, m.threshold,
+                                   m.depth_points, C.c_void_p(m.workspace.data_ptr()), nbytes.value,
+                                   C.c_void_p(m.result.data_ptr()), _stream(device)), "cnrma_rma_march")
+    return m
+
+
+def _read_result(m):
+    """The one host sync of the path: M (and the weight sum) back to the host."""
+    raw = bytes(m.result.cpu().numpy().tobytes())
+    res = _lib.RmaResult.from_buffer_copy(raw)
+    if res.overflow:
+        raise CnrmaError(f"{res.overflow} rays exceeded the per-ray record capacity")
+    return res
+
+
+def _fill(fs, b, m, grid, rows_host, normalize, mean_tensor=None):
+    lib = _lib.load()
+    device = fs.device
+    cols = fs.C + (3 if normalize else 4)
+    rows = torch.empty((rows_host, cols), dtype=torch.float32, device=device)
+    if rows_host == 0:
+        return rows
+    desc = fs.descriptor(b)
+    mean_ptr = C.c_void_p(mean_tensor.data_ptr()) if mean_tensor is not None else None
+    _lib.check(lib.cnrma_rma_fill(C.byref(grid), C.c_void_p(m.pinv.data_ptr()), C.byref(desc), m.grids, m.t_one,
+                                  m.mode, m.threshold, m.depth_points, C.c_void_p(m.workspace.data_ptr()),
+                                  C.c_void_p(m.result.data_ptr()), rows_host, 1 if normalize else 0, mean_ptr,
+                                  C.c_void_p(rows.data_ptr()), cols, rows_host, _stream(device)), "cnrma_rma_fill")
+    return rows
+
+
+def _check_mode(mode, threshold, depth_points):
+    if mode == "neus":
+        if threshold is None:
+            raise ValueError("neus ray marching needs a weight threshold (rm.py:191)")
+    elif mode == "depth":
+        if depth_points is None or depth_points < 0:
+            raise ValueError("depth ray marching needs depth_points >= 0")
+    else:
+        raise ValueError("ray_marching_type must be 'neus' or 'depth'")
+
+
+def rma_points(projections, features, tsdf, voxel_dim, voxel_size, origin, stride, grids=300, mode="neus",
+               threshold=None, depth_points=None, normalize=True, return_stats=False, mean_hook=None):
+    """aggregate_2d_features_ray_marching (rm.py:260-307) for all views at once.
+
+    projections [V,B,3,4] un-scaled, features [V,B,C,H,W] (or sequence of [B,C,H,W]), tsdf [B,1,nx,ny,nz].
+    Returns a list over the batch of [M,3+C] tensors (rows [x,y,z, feat*w/mean(w)] in (view, v, u, step)
+    order); with normalize=False the un-normalised [M,4+C] rows ([x,y,z,w,feat]) the per-view function
+    returns.  A batch element with no kept sample yields an empty [0, .] tensor (the reference raises).
+    `mean_hook(weight_sum, rows, device) -> float32 CUDA tensor [1]` overrides the divisor of rm.py:303."""
+    _check_mode(mode, threshold, depth_points)
+    fs = _FeatureStack(_as_view_list(features), need_vector_layout=False)
+    device = fs.device
+    if not isinstance(projections, torch.Tensor):
+        projections = torch.stack(list(projections), dim=0)
+    P_scaled = scale_projections(projections, stride)            # host, [V,B,3,4]
+    grid = _lib.make_grid(voxel_dim, voxel_size, _origin3(origin))
+    out, stats = [], []
+    with torch.cuda.device(device):
+        for b in range(fs.B):
+            m = _march(fs, b, P_scaled[:, b], tsdf[b, 0], grid, voxel_dim, voxel_size, grids, mode, threshold,
+                       depth_points)
+            res = _read_result(m)
+            # view-sharded callers replace the local mean weight by the all-reduced one (distributed.py)
+            mean_t = mean_hook(res.weight_sum, res.rows, device) if (mean_hook and normalize) else None
+            out.append(_fill(fs, b, m, grid, int(res.rows), normalize, mean_t))
+            stats.append(dict(rows=int(res.rows), weight_sum=float(res.weight_sum), mean=float(res.mean)))
+    return (out, stats) if return_stats else out
+
+
+def ray_projection(projection, features, tsdf, voxel_dim, voxel_size, origin, grids=300, mode="neus",
+                   threshold=None, depth_points=None):
+    """ray_projection_neus / ray_projection_depth for ONE view (rm.py:687-807 / :809-956).
+    projection [B,3,4] already stride-scaled, features [B,C,H,W] -> list over b of [M,4+C], or None if any
+    batch element keeps no sample (rm.py:782-783)."""
+    rows = rma_points(projection.unsqueeze(0), features.unsqueeze(0), tsdf, voxel_dim, voxel_size, origin, 1.0,
+                      grids=grids, mode=mode, threshold=threshold, depth_points=depth_points, normalize=False)
+    if any(r.shape[0] == 0 for r in rows):
+        return None
+    return rows
+
+
+def rma_dense_weights(projections, height, width, tsdf, voxel_dim, voxel_size, origin, stride, grids=300,
+                      threshold=0.05, device=None):
+    """Parity surface for rm.py:765-767: (weights * valid_final, valid_final), each [V,H,W,N], batch 1."""
+    lib = _lib.load()
+    device = torch.device(device) if device is not None else tsdf.device
+
+    class _Shape:
+        pass
+    fs = _Shape()
+    fs.device, fs.V, fs.H, fs.W = device, projections.shape[0], int(height), int(width)
+    P_scaled = scale_projections(projections, stride)
+    grid = _lib.make_grid(voxel_dim, voxel_size, _origin3(origin))
+    with torch.cuda.device(device):
+        m = _march(fs, 0, P_scaled[:, 0], tsdf[0, 0], grid, voxel_dim, voxel_size, grids, "neus", threshold, None)
+        n = fs.V * fs.H * fs.W * int(grids)
+        w = torch.empty(n, dtype=torch.float32, device=device)
+        keep = torch.empty(n, dtype=torch.bool, device=device)
+        _lib.check(lib.cnrma_rma_expand(fs.V, fs.H, fs.W, int(grids), float(threshold),
+                                        C.c_void_p(m.workspace.data_ptr()), C.c_void_p(w.data_ptr()),
+                                        C.c_void_p(keep.data_ptr()), _stream(device)), "cnrma_rma_expand")
+        _read_result(m)
+    shape = (fs.V, fs.H, fs.W, int(grids))
+    return w.view(shape), keep.view(shape)
+
+
+def dense_rma(projections, features, tsdf, voxel_dim, voxel_size, origin, stride, grids=300, mode="neus",
+              threshold=None, depth_points=None, out=None):
+    """Derived dense operator: per-voxel weighted feature sums and weight totals of the RMA lift.
+
+    Returns (wsum [B,C,nx,ny,nz] fp32 (channels_last_3d view), wtot [B,1,nx,ny,nz] fp32), un-normalised so
+    that view-sharded partial results add (one all-reduce, see distributed.py).  `out=(wsum, wtot)`
+    accumulates into existing buffers."""
+    _check_mode(mode, threshold, depth_points)
+    lib = _lib.load()
+    fs = _FeatureStack(_as_view_list(features), need_vector_layout=False)
+    device = fs.device
+    if not isinstance(projections, torch.Tensor):
+        projections = torch.stack(list(projections), dim=0)
+    P_scaled = scale_projections(projections, stride)
+    nx, ny, nz = (int(v) for v in voxel_dim)
+    grid = _lib.make_grid(voxel_dim, voxel_size, _origin3(origin))
+    if out is None:
+        buf = torch.zeros((fs.B, nx, ny, nz, fs.C), dtype=torch.float32, device=device)
+        wtot = torch.zeros((fs.B, 1, nx, ny, nz), dtype=torch.float32, device=device)
+        wsum = buf.permute(0, 4, 1, 2, 3)
+    else:
+        wsum, wtot = out
+        if wsum.stride(1) != 1 or not wtot.is_contiguous():
+            raise ValueError("out buffers must be channels-last wsum and contiguous wtot")
+    with torch.cuda.device(device):
+        for b in range(fs.B):
+            m = _march(fs, b, P_scaled[:, b], tsdf[b, 0], grid, voxel_dim, voxel_size, grids, mode, threshold,
+                       depth_points)
+            desc = fs.descriptor(b)
+            _lib.check(lib.cnrma_rma_scatter(C.byref(grid), C.c_void_p(m.pinv.data_ptr()), C.byref(desc), m.grids,
+                                             m.t_one, m.mode, m.threshold, m.depth_points,
+                                             C.c_void_p(m.workspace.data_ptr()), C.c_void_p(wsum[b].data_ptr()),
+                                             C.c_void_p(wtot[b].data_ptr()), _stream(device)), "cnrma_rma_scatter")
+    return wsum, wtot

@@ -1,0 +1,179 @@
+/*
+ * cnrma_b200.h -- C ABI of libcnrma_b200.so: CN-RMA's ray-marching aggregation (the 2D -> 3D feature
+ * lift) as hand-written sm_100a CUDA kernels.
+ *
+ * The reference (SerCharles/CN-RMA) is pure PyTorch and has no FFI; the interface each entry point
+ * replaces is therefore a Python function of projects/mvsdetection/models/ray_marching.py ("rm.py").
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer unless its name ends in `_host`.
+ *   - The caller owns all memory (PyTorch in practice); the library never allocates device memory and
+ *     keeps no global state.  Scratch space is sized by the *_workspace_bytes queries.
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises except
+ *     where stated.  Safe to call concurrently from several host threads on different streams.
+ *   - Return value: CNRMA_OK (0) or a negative cnrma_status; CUDA runtime errors are returned as
+ *     CNRMA_ERR_CUDA and the cudaError_t is available from cnrma_last_cuda_error().
+ *   - There is no CPU path.  A device that is not compute capability 10.x gets CNRMA_ERR_DEVICE.
+ *   - Voxel order is the reference's: flat = (x*ny + y)*nz + z (datasets/tsdf.py:24-29).
+ */
+#ifndef CNRMA_B200_H
+#define CNRMA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNRMA_ABI_VERSION 1
+
+typedef enum cnrma_status {
+    CNRMA_OK = 0,
+    CNRMA_ERR_ARG = -1,       /* null pointer, non-positive dimension, unknown enum value */
+    CNRMA_ERR_LAYOUT = -2,    /* feature maps not channels-last / not 16-byte aligned for the vector path */
+    CNRMA_ERR_CAPACITY = -3,  /* caller-provided buffer or workspace too small */
+    CNRMA_ERR_DEVICE = -4,    /* current device is not sm_100-class */
+    CNRMA_ERR_CUDA = -5,      /* a CUDA runtime call failed: see cnrma_last_cuda_error() */
+    CNRMA_ERR_UNSUPPORTED = -6
+} cnrma_status;
+
+typedef enum cnrma_dtype { CNRMA_F32 = 0, CNRMA_BF16 = 1 } cnrma_dtype;
+
+/* The voxel volume: RayMarching.voxel_dim / voxel_size / origin (rm.py:166-184). */
+typedef struct cnrma_grid {
+    int32_t nx, ny, nz;
+    float voxel_size;
+    float origin[3];
+} cnrma_grid;
+
+/* A stack of per-view feature maps (the `features` argument of rm.py:21 / :220 / :260 / :687).
+ * view_ptrs_host is a HOST array of `views` DEVICE pointers, one per view's [C,H,W] map, so views that
+ * live in separate tensors need no concatenation.  Strides are in elements.  The gather kernels
+ * require channels-last maps: stride_c == 1, stride_x % 4 == 0 (f32) or % 8 == 0 (bf16), 16-byte
+ * aligned bases; use cnrma_to_channels_last() first for NCHW inputs. */
+typedef struct cnrma_features {
+    int32_t views, channels, height, width;
+    int32_t dtype; /* cnrma_dtype */
+    int64_t stride_c, stride_y, stride_x;
+    const void *const *view_ptrs_host;
+} cnrma_features;
+
+/* Flags of cnrma_aggregate_views. */
+#define CNRMA_AGG_ACCUMULATE 1u /* add to the sums/counts already in volume/count (rm.py:243-244) */
+#define CNRMA_AGG_MEAN 2u       /* finish with volume/count, 0 where count==0 (rm.py:247-257) */
+#define CNRMA_AGG_COUNT_F32 4u  /* `count` holds float32 (exact below 2^24): lets sums and counts share one
+                                   fp32 all-reduce buffer when views are sharded across GPUs */
+
+/* Ray-march flavours (RayMarching.ray_marching_type, rm.py:188-194). */
+typedef enum cnrma_march_mode { CNRMA_MARCH_NEUS = 0, CNRMA_MARCH_DEPTH = 1 } cnrma_march_mode;
+
+/* Result block written by cnrma_rma_march (device memory, 32 bytes). */
+typedef struct cnrma_rma_result {
+    int64_t rows;     /* M: kept samples over all views */
+    double weight_sum; /* sum of their weights */
+    float mean;       /* (float)(weight_sum / rows), the divisor of rm.py:303 */
+    int32_t overflow; /* rays whose kept-sample count exceeded the per-ray record capacity (must be 0) */
+} cnrma_rma_result;
+
+int cnrma_abi_version(void);
+const char *cnrma_status_string(int status);
+int cnrma_last_cuda_error(void);
+/* CNRMA_OK when the current CUDA device can run the kernels (compute capability 10.x). */
+int cnrma_check_device(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage A -- dense back-projection (voxel driven)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Replaces the index/mask part of backproject(), rm.py:47-58, for V views at once.
+ *   projections  [V] 3x4 row-major matrices, UN-scaled; element stride between views = proj_view_stride
+ *   stride       RayMarching.backbone2d_stride: rows 0-1 are divided by it first (rm.py:238-239)
+ *   px, py       int32 [V, nvox]: round(x/z), round(y/z); 0 where !valid
+ *   valid        uint8 [V, nvox]: px>=0 & py>=0 & px<W & py<H & pz>0
+ * Any of px / py / valid may be NULL.  Bit-exact with the reference on CPU. */
+int cnrma_project_views(const cnrma_grid *grid, const float *projections, int64_t proj_view_stride, int views,
+                        float stride, int height, int width, int32_t *px, int32_t *py, uint8_t *valid,
+                        void *stream);
+
+/* Replaces  V x aggregate_2d_features (rm.py:220-244; backproject rm.py:21-69 inside it)  and, with
+ * CNRMA_AGG_MEAN, clear_3d_features (rm.py:247-257) -- one fused pass: project, mask, nearest gather,
+ * sum over views in view order (fp32, so bit-exact with the reference's running sum), divide.
+ *   volume  f32, element (voxel, c) at volume[voxel*vol_stride_voxel + c*vol_stride_channel]
+ *           ([nvox,C] channels-last: (C,1);  the reference's NCDHW: (1,nvox))
+ *   count   int32 [nvox] number of views that see the voxel (self.valid before clear_3d_features)
+ *   valid   uint8 [nvox] count > 0 (self.valid after clear_3d_features); may be NULL
+ * With V = 1 and flags = 0 this is backproject() itself.  features->views may be 0 together with
+ * CNRMA_AGG_ACCUMULATE | CNRMA_AGG_MEAN: a finalise-only pass over sums and counts produced elsewhere
+ * (e.g. after an all-reduce of view-sharded partial results). */
+int cnrma_aggregate_views(const cnrma_grid *grid, const cnrma_features *features, const float *projections,
+                          int64_t proj_view_stride, float stride, uint32_t flags, float *volume,
+                          int64_t vol_stride_voxel, int64_t vol_stride_channel, int32_t *count, uint8_t *valid,
+                          void *stream);
+
+/* Layout helper for reference-layout (NCHW) feature maps: src [V][C,H,W] with the given strides ->
+ * dst channels-last [V,H,W,C] contiguous, same dtype.  One read + one write of the features. */
+int cnrma_to_channels_last(const cnrma_features *src, void *dst, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage B -- ray marching aggregation (ray driven)
+ * ------------------------------------------------------------------------------------------- */
+
+/* t_one of rm.py:710-711 evaluated like the reference (python doubles, then one rounding to float). */
+float cnrma_t_one(const cnrma_grid *grid, double voxel_size, int grids);
+
+/* Replaces get_ray_parameter (rm.py:71-111) as tensors: o, d f32 [V,3,H*W] from pinv [V] 4x4 (see
+ * cnrma_rma_march for how pinv is obtained).  The march / fill kernels recompute the same values inline. */
+int cnrma_ray_parameters(const float *pinv, int views, int height, int width, float *o, float *d, void *stream);
+
+/* Bytes of scratch cnrma_rma_march / _fill / _scatter need for `views` x H x W rays. */
+int cnrma_rma_workspace_bytes(int views, int height, int width, int grids, int mode, float threshold,
+                              int depth_points, size_t *bytes);
+
+/* Replaces get_ray_parameter (rm.py:71-111; the 4x4 inverses are an input, see below) and the march /
+ * weight / selection part of ray_projection_neus (rm.py:710-767) or ray_projection_depth
+ * (rm.py:826-911) for all V views (batch 1, like the reference, rm.py:707).
+ *   pinv       [V] 4x4 row-major inverse of [P_scaled; 0 0 0 1] (rm.py:96-102).  The host computes it with
+ *              the same LAPACK call as the reference (torch.inverse) so ray parameters stay bit-exact.
+ *   tsdf       f32 [nx,ny,nz]
+ *   grids      N, samples per ray (rm.py:687 default 300);  t_one from cnrma_t_one()
+ *   threshold  weight_threshold / neus_threshold (NEUS);  depth_points = select_grids (DEPTH)
+ *   result     device cnrma_rma_result: rows, weight sum, mean.  Read result->rows back (the one sync
+ *              of the path; the reference syncs once per view at rm.py:781-782) to size the output.
+ * Sample order is the reference's: ascending (view, v, u, step). */
+int cnrma_rma_march(const cnrma_grid *grid, const float *pinv, int views, int height, int width,
+                    const float *tsdf, int grids, float t_one, int mode, float threshold, int depth_points,
+                    void *workspace, size_t workspace_bytes, cnrma_rma_result *result, void *stream);
+
+/* Replaces the compaction + feature gather of rm.py:769-807 and, with normalize != 0, the concat +
+ * weight normalisation of aggregate_2d_features_ray_marching (rm.py:289-307).
+ *   rows        f32 [M, row_stride]; columns  normalize ? [x,y,z, feat*w/mean] : [x,y,z,w, feat]
+ *   mean        device float used as the divisor when normalize != 0; NULL = result->mean of the march
+ *               (a view-sharded caller passes the all-reduced mean here)
+ *   capacity    rows the buffer can hold; CNRMA_ERR_CAPACITY is returned (host-side check against
+ *               rows_host) if smaller than M
+ * grids / mode / threshold / depth_points must repeat the march call's values (they fix the workspace
+ * layout).  Features need stride_c == 1; no alignment requirement. */
+int cnrma_rma_fill(const cnrma_grid *grid, const float *pinv, const cnrma_features *features, int grids,
+                   float t_one, int mode, float threshold, int depth_points, const void *workspace,
+                   const cnrma_rma_result *result, int64_t rows_host, int normalize, const float *mean,
+                   float *rows, int64_t row_stride, int64_t capacity, void *stream);
+
+/* Derived dense operator (north_star's output form; SURVEY.md section 8a "dense_rma"): instead of
+ * emitting rows, adds w*feat into wsum[voxel, :] and w into wtot[voxel] for the voxel each kept sample
+ * rounds to (rm.py:730).  wsum f32 [nvox, C] channels-last, wtot f32 [nvox]; both are accumulated into
+ * (zero them first; partial results from view shards add).  fp32 atomics: order-dependent rounding. */
+int cnrma_rma_scatter(const cnrma_grid *grid, const float *pinv, const cnrma_features *features, int grids,
+                      float t_one, int mode, float threshold, int depth_points, const void *workspace, float *wsum,
+                      float *wtot, void *stream);
+
+/* Dense per-sample view of the march records for parity tests: weights f32 [V*H*W*N] (0 where not kept,
+ * i.e. rm.py:767 `weights * valid_final`) and keep uint8 [V*H*W*N].  NEUS mode only. */
+int cnrma_rma_expand(int views, int height, int width, int grids, float threshold, const void *workspace,
+                     float *weights, uint8_t *keep, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNRMA_B200_H */

@@ -110,40 +110,63 @@ ORACLE_API void cnrma_oracle_project(int nx, int ny, int nz, float voxel_size, c
  *   rm.py:220-244 aggregate_2d_features (volume += v; valid += mask, in view order)
  *   rm.py:247-257 clear_3d_features (volume / count, 0 where count == 0) when `mean` != 0
  * projections: [V,3,4] UN-scaled; features: [V,C,H,W] (NCHW); volume: [C,nvox]; count: int64 [nvox].
- */
+ *
+ * Loop order follows the reference's data flow (per view: indices once, then every channel plane gathered
+ * through them), which is also the cache-friendly order for NCHW maps: phase 1 builds, per view, the list of
+ * (voxel, pixel offset) pairs inside the frustum; phase 2 walks channels in parallel and, for each channel,
+ * the views in order -- so every volume element still receives its additions in view order (bit-exact with
+ * the reference's running sum; the zeros it adds for invisible views do not change an fp32 sum that starts
+ * at +0). */
 ORACLE_API void cnrma_oracle_aggregate_views(int V, int C, int H, int W, int nx, int ny, int nz, float voxel_size,
                                              const float *origin, float stride, const float *projections,
                                              const float *features, int mean, float *volume, int64_t *count) {
     size_t nvox = (size_t)nx * ny * nz;
     size_t plane = (size_t)H * W;
-    float *P = (float *)malloc(sizeof(float) * 12 * (size_t)V);
+    float *P = (float *)malloc(sizeof(float) * 12 * (size_t)(V > 0 ? V : 1));
+    int32_t **vox_list = (int32_t **)calloc((size_t)(V > 0 ? V : 1), sizeof(int32_t *));
+    int32_t **off_list = (int32_t **)calloc((size_t)(V > 0 ? V : 1), sizeof(int32_t *));
+    size_t *n_list = (size_t *)calloc((size_t)(V > 0 ? V : 1), sizeof(size_t));
     for (int v = 0; v < V; ++v) cnrma_oracle_scale_projection(projections + 12 * v, stride, P + 12 * v);
-#pragma omp parallel
-    {
-        float *acc = (float *)malloc(sizeof(float) * (size_t)C);
-#pragma omp for collapse(2) schedule(static)
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int v = 0; v < V; ++v) {
+        int32_t *vl = (int32_t *)malloc(sizeof(int32_t) * nvox);
+        int32_t *ol = (int32_t *)malloc(sizeof(int32_t) * nvox);
+        size_t n = 0;
         for (int x = 0; x < nx; ++x)
             for (int y = 0; y < ny; ++y)
                 for (int z = 0; z < nz; ++z) {
-                    size_t i = ((size_t)x * ny + y) * nz + z;
-                    int64_t n = 0;
-                    for (int c = 0; c < C; ++c) acc[c] = 0.0f;
-                    for (int v = 0; v < V; ++v) {
-                        int64_t px, py;
-                        if (!project_voxel(P + 12 * v, voxel_size, origin, x, y, z, H, W, &px, &py)) continue;
-                        const float *f = features + (size_t)v * C * plane + (size_t)py * W + (size_t)px;
-                        for (int c = 0; c < C; ++c) acc[c] = acc[c] + f[(size_t)c * plane];
-                        ++n;
-                    }
-                    count[i] = n;
-                    for (int c = 0; c < C; ++c) {
-                        float s = acc[c];
-                        if (mean) s = (n > 0) ? s / (float)n : 0.0f;
-                        volume[(size_t)c * nvox + i] = s;
-                    }
+                    int64_t px, py;
+                    if (!project_voxel(P + 12 * v, voxel_size, origin, x, y, z, H, W, &px, &py)) continue;
+                    vl[n] = (int32_t)(((size_t)x * ny + y) * nz + z);
+                    ol[n] = (int32_t)(py * W + px);
+                    ++n;
                 }
-        free(acc);
+        vox_list[v] = vl;
+        off_list[v] = ol;
+        n_list[v] = n;
     }
+    for (size_t i = 0; i < nvox; ++i) count[i] = 0;
+    for (int v = 0; v < V; ++v)
+        for (size_t k = 0; k < n_list[v]; ++k) count[vox_list[v][k]] += 1;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int c = 0; c < C; ++c) {
+        float *acc = volume + (size_t)c * nvox;
+        for (size_t i = 0; i < nvox; ++i) acc[i] = 0.0f;
+        for (int v = 0; v < V; ++v) {
+            const float *f = features + ((size_t)v * C + c) * plane;
+            const int32_t *vl = vox_list[v], *ol = off_list[v];
+            for (size_t k = 0; k < n_list[v]; ++k) acc[vl[k]] = acc[vl[k]] + f[ol[k]];
+        }
+        if (mean)
+            for (size_t i = 0; i < nvox; ++i) acc[i] = (count[i] > 0) ? acc[i] / (float)count[i] : 0.0f;
+    }
+    for (int v = 0; v < V; ++v) {
+        free(vox_list[v]);
+        free(off_list[v]);
+    }
+    free(vox_list);
+    free(off_list);
+    free(n_list);
     free(P);
 }
 
