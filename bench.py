@@ -212,9 +212,11 @@ def main():
     # --- one step, with CUDA events between the phases (all on the current stream) ---------------------
     fs = F._FeatureStack(F._as_view_list(feats), need_vector_layout=True)
     grid = _lib.make_grid(sc.voxel_dim, sc.voxel_size, sc.origin)
-    P_scaled = F.scale_projections(proj, sc.stride)
 
     def step(ev=None):
+        # host half of the ray set-up first (4x4 LAPACK inverses, rm.py:96-102), so that it overlaps with the
+        # GPU work already queued instead of delaying the march launch
+        pinv = F.prepare_pinv(F.scale_projections(proj, sc.stride)[:, 0], dev) if args.stage in ("both", "b") else None
         if ev:
             ev[0].record()
         out_a = None
@@ -224,8 +226,8 @@ def main():
             ev[1].record()
         rows, m_rows = None, 0
         if args.stage in ("both", "b"):
-            m = F._march(fs, 0, P_scaled[:, 0], tsdf[0, 0], grid, sc.voxel_dim, sc.voxel_size, sc.grids, "neus", thr,
-                         None)
+            m = F._march(fs, 0, None, tsdf[0, 0], grid, sc.voxel_dim, sc.voxel_size, sc.grids, "neus", thr, None,
+                         pinv=pinv)
             if ev:
                 ev[2].record()
             res = F._read_result(m)              # the path's one host sync: M sizes the output

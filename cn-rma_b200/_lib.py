@@ -80,6 +80,7 @@ _SIGNATURES = {
     "cnrma_aggregate_views": (C.c_int, [C.POINTER(Grid), C.POINTER(Features), C.c_void_p, C.c_int64, C.c_float,
                                         C.c_uint32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_void_p]),
+    "cnrma_selftest_count_division": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
     "cnrma_to_channels_last": (C.c_int, [C.POINTER(Features), C.c_void_p, C.c_void_p]),
     "cnrma_t_one": (C.c_float, [C.POINTER(Grid), C.c_double, C.c_int]),
     "cnrma_ray_parameters": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -96,9 +96,9 @@ int cnrma_aggregate_views(const cnrma_grid *grid, const cnrma_features *features
     if (fs != CNRMA_OK) return fs;
     const int d = device_ok();
     if (d != CNRMA_OK) return d;
-    // Tuning knob (DESIGN.md "K_A"): cap on 16-byte vectors per channel pass; 0 = whole rows in one pass.
+    // Tuning knob (DESIGN.md "K_A"): cap on the bytes of a feature row gathered per channel pass (<= 1024).
     int max_chunk_vecs = 0;
-    if (const char *env = std::getenv("CNRMA_AGG_CHUNK_VECS")) max_chunk_vecs = std::atoi(env);
+    if (const char *env = std::getenv("CNRMA_AGG_CHUNK_BYTES")) max_chunk_vecs = std::atoi(env);
     const GridDev g = to_dev(*grid);
     for (int v0 = 0; v0 < features->views || v0 == 0; v0 += kMaxViewsPerLaunch) {
         const int nv = (features->views - v0 < kMaxViewsPerLaunch) ? (features->views - v0) : kMaxViewsPerLaunch;
@@ -112,6 +112,15 @@ int cnrma_aggregate_views(const cnrma_grid *grid, const cnrma_features *features
         if (e != cudaSuccess) return fail_cuda(e);
     }
     return CNRMA_OK;
+}
+
+int cnrma_selftest_count_division(int max_n, uint64_t *mismatches, void *stream) {
+    if (!mismatches || max_n < 1 || max_n > 65535) return CNRMA_ERR_ARG;
+    const int d = device_ok();
+    if (d != CNRMA_OK) return d;
+    const cudaError_t e = run_selftest_count_division(max_n, reinterpret_cast<unsigned long long *>(mismatches),
+                                                      static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
 }
 
 int cnrma_to_channels_last(const cnrma_features *src, void *dst, void *stream) {

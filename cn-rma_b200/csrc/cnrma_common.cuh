@@ -93,6 +93,12 @@ struct Vec16<float> {
         r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
         return r;
     }
+    __device__ __forceinline__ static Vec16 load_shared(const void *p) {
+        const float4 t = *reinterpret_cast<const float4 *>(p);
+        Vec16 r;
+        r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+        return r;
+    }
 };
 
 template <>
@@ -100,7 +106,10 @@ struct Vec16<__nv_bfloat16> {
     static constexpr int kElems = 8;
     float v[8];
     __device__ __forceinline__ static Vec16 load(const __nv_bfloat16 *p) {
-        const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p));
+        return widen(__ldg(reinterpret_cast<const uint4 *>(p)));
+    }
+    __device__ __forceinline__ static Vec16 load_shared(const void *p) { return widen(*reinterpret_cast<const uint4 *>(p)); }
+    __device__ __forceinline__ static Vec16 widen(const uint4 t) {
         Vec16 r;
         const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll

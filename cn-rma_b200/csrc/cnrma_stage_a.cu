@@ -1,18 +1,26 @@
 // Stage A: dense back-projection -- voxel->pixel projection, frustum mask, nearest gather and the
 // multi-view sum / mean, fused into one pass (reference: rm.py:21-69, :220-257).
 //
-// Work decomposition of the gather kernel (DESIGN.md "K_A"):
-//   * a group of G lanes owns one voxel and a `chunk` of G*VPL 16-byte vectors of its channels; a warp
-//     carries 32/G voxels.  For C = 256 fp32: G = 32, VPL = 2, one voxel per warp, two LDG.128 per lane
-//     per visible view -- every gather is one fully coalesced 1 KB row of the channels-last map.
-//   * the lanes of a group project their voxel through G views at a time (lane <-> view), a ballot turns
-//     the frustum tests into a bit mask, and the set bits are walked in ascending view order, so the fp32
-//     sum is formed in exactly the order of the reference's `self.volume + volume` loop.
-//   * up to kUnroll gathers are issued before the first add to keep several 16-byte loads in flight
-//     per lane.
+// Design of the gather kernel (DESIGN.md "K_A"):
+//   * persistent warps; one warp owns one voxel at a time and walks the views 32 at a time, lane <-> view:
+//     every lane projects the voxel through its view (explicit FMA chain, IEEE division, rint -- bit-exact
+//     with the reference), a ballot turns the frustum tests into a bit mask.
+//   * each lane whose view sees the voxel issues ONE bulk asynchronous copy (TMA, cp.async.bulk
+//     global -> shared, completion on the warp's mbarrier) of the pixel's channels-last feature row --
+//     1 KB for 256 fp32 channels -- into the warp's row buffer, at the slot given by its rank among the
+//     visible views.  No registers are tied up by loads in flight and a 1 KB gather costs one instruction
+//     instead of 64 LDG.128; with 32 resident warps per SM up to ~190 KB of gathers are in flight per SM.
+//   * when the buffer is full (or the views are exhausted) the warp waits on the mbarrier and adds the rows
+//     from shared memory in slot order == view order, so the fp32 sum is formed exactly like the
+//     reference's `self.volume + volume` loop (conflict-free LDS.128, lane <-> 4 channels).
 //   * camera matrices (pre-divided by the backbone stride) and per-view base pointers sit in shared
 //     memory, matrices as structure-of-arrays so that lane <-> view reads are conflict free.
-//   * blockIdx.y walks channel chunks (pass-major CTA order) when C exceeds one chunk.
+//   * the count-mean divides by a small integer: one correctly rounded reciprocal per voxel and a
+//     Markstein correction step per channel give the IEEE quotient (verified exhaustively by
+//     cnrma_selftest_count_division) at a quarter of the instructions of eight generic divisions.
+//   * blockIdx.y walks channel chunks (pass-major CTA order) when a feature row exceeds kMaxChunkBytes.
+#include <cstdlib>
+
 #include "cnrma_internal.cuh"
 
 namespace cnrma {
@@ -33,23 +41,70 @@ struct AggParams {
     int vec_store;                // volume is channels-last and 16-byte aligned
     int chunk_base;               // first channel chunk of this launch (added to blockIdx.y)
     int write_count;              // this launch owns count/valid (see run_aggregate)
+    int chunk_bytes;              // bytes of a feature row handled per pass (multiple of 16, <= kMaxChunkBytes)
+    int rows_cap;                 // row slots per warp buffer
+    int order;                    // 0: sweep z-slices, 1: flat voxel order
     const void *views[kMaxViewsPerLaunch];
 };
 
+constexpr int kMaxChunkBytes = 1024;     // 64 16-byte vectors: two per lane
+constexpr int kWarpBufferBytes = 6144;   // per-warp row buffer: 4 CTAs x 8 warps x 6 KB = 192 KB per SM
+constexpr int kAggCtasPerSm = 4;
 
-template <int G, int VPL, typename T>
-__global__ void __launch_bounds__(kAggThreads) aggregate_views_kernel(const __grid_constant__ AggParams p) {
+// ---- mbarrier / bulk-copy primitives (PTX) ---------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> this CTA's shared memory, completion (bytes) signalled on `bar`.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// IEEE-correct a / n for a small positive integer n, given y = RN(1/n): q = RN(a*y); r = a - n*q (exact, FMA);
+// q' = RN(q + r*y) (Markstein).  Values whose residual could leave the normal range take the generic path.
+__device__ __forceinline__ float div_by_count(float a, float n, float y) {
+    const float mag = fabsf(a);
+    if (!(mag > 1e-30f && mag < 1e30f)) return __fdiv_rn(a, n);
+    const float q = __fmul_rn(a, y);
+    const float r = __fmaf_rn(-n, q, a);
+    return __fmaf_rn(r, y, q);
+}
+
+template <int VPL, typename T>
+__global__ void __launch_bounds__(kAggThreads, kAggCtasPerSm)
+aggregate_views_kernel(const __grid_constant__ AggParams p) {
     using V16 = Vec16<T>;
-    constexpr int E = V16::kElems;             // channels per 16-byte vector
-    constexpr int kVoxPerWarp = kWarp / G;
-    constexpr unsigned kGroupMask = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
-    // gathers issued back to back before the first add: bounded so the staging registers stay <= 32 floats
-    constexpr int kUnroll = (32 / (VPL * E)) > 0 ? (32 / (VPL * E)) : 1;
+    constexpr int E = V16::kElems;   // channels per 16-byte vector
+    constexpr int kWarps = kAggThreads / kWarp;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int Vpad = p.V | 1;                  // odd stride: conflict-free lane<->view reads
-    const T **sView = reinterpret_cast<const T **>(smem_raw);                        // [V]
-    float *sP = reinterpret_cast<float *>(smem_raw + sizeof(void *) * p.V);          // [12][Vpad]
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int Vpad = p.V | 1;   // odd stride: conflict-free lane<->view reads
+    uint64_t *sBar = reinterpret_cast<uint64_t *>(smem_raw);                                   // [kWarps]
+    const unsigned char **sView = reinterpret_cast<const unsigned char **>(smem_raw + 8 * kWarps);   // [V]
+    float *sP = reinterpret_cast<float *>(smem_raw + 8 * kWarps + sizeof(void *) * p.V);       // [12][Vpad]
+    const size_t head = (8 * kWarps + sizeof(void *) * p.V + sizeof(float) * 12 * Vpad + 127) & ~(size_t)127;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    unsigned char *rowbuf = smem_raw + head + (size_t)warp * p.rows_cap * p.chunk_bytes;
 
     for (int i = threadIdx.x; i < 12 * p.V; i += blockDim.x) {
         const int v = i / 12, k = i % 12;
@@ -57,184 +112,205 @@ __global__ void __launch_bounds__(kAggThreads) aggregate_views_kernel(const __gr
         if (k < 8) val = __fdiv_rn(val, p.stride);   // rows 0-1 / stride (rm.py:238-239)
         sP[k * Vpad + v] = val;
     }
-    for (int i = threadIdx.x; i < p.V; i += blockDim.x) sView[i] = static_cast<const T *>(p.views[i]);
+    const int chunk = p.chunk_base + blockIdx.y;
+    for (int i = threadIdx.x; i < p.V; i += blockDim.x)
+        sView[i] = static_cast<const unsigned char *>(p.views[i]) + (size_t)chunk * p.chunk_bytes;
+    if (threadIdx.x < kWarps) mbar_init(smem_u32(&sBar[threadIdx.x]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int grp = lane / G;
-    const int lig = lane % G;
-    const int vox = (blockIdx.x * (kAggThreads / kWarp) + warp) * kVoxPerWarp + grp;
-    const bool vox_ok = vox < p.nvox;
-    const int c0 = ((p.chunk_base + blockIdx.y) * (G * VPL) + lig) * E;   // first channel of this lane
+    const uint32_t bar = smem_u32(&sBar[warp]);
+    const uint32_t buf0 = smem_u32(rowbuf);
+    const int nvec = p.chunk_bytes >> 4;
+    const int c0 = chunk * (p.chunk_bytes / (int)sizeof(T));   // first channel of this pass
+    const int esz = (int)sizeof(T);
+    uint32_t parity = 0;
 
-    // voxel order of datasets/tsdf.py:24-29: flat = (x*ny + y)*nz + z
-    const int vz = vox % p.g.nz;
-    const int vxy = vox / p.g.nz;
-    const int vy = vxy % p.g.ny;
-    const int vx = vxy / p.g.ny;
-    const float wx = world_coord(vx, p.g.vs, p.g.ox);
-    const float wy = world_coord(vy, p.g.vs, p.g.oy);
-    const float wz = world_coord(vz, p.g.vs, p.g.oz);
-
-    float acc[VPL][E];
-    int cnt = 0;
-    if ((p.flags & CNRMA_AGG_ACCUMULATE) && vox_ok) {
-        cnt = (p.flags & CNRMA_AGG_COUNT_F32) ? (int)reinterpret_cast<const float *>(p.count)[vox] : p.count[vox];
-#pragma unroll
-        for (int k = 0; k < VPL; ++k)
-#pragma unroll
-            for (int e = 0; e < E; ++e)
-                acc[k][e] = p.volume[(int64_t)vox * p.vsv + (int64_t)(c0 + k * G * E + e) * p.vsc];
-    } else {
-#pragma unroll
-        for (int k = 0; k < VPL; ++k)
-#pragma unroll
-            for (int e = 0; e < E; ++e) acc[k][e] = 0.0f;
-    }
-
-    for (int v0 = 0; v0 < p.V; v0 += G) {
-        const int view = v0 + lig;
-        int off = -1;
-        if (view < p.V && vox_ok) {
-            int px, py;
-            if (project_voxel(sP + view, Vpad, wx, wy, wz, p.H, p.W, px, py))
-                off = (int)(py * p.stride_y + px * p.stride_x);
+    const int warps_total = gridDim.x * kWarps;
+    const int nxy = p.g.nx * p.g.ny;
+    for (int it = blockIdx.x * kWarps + warp; it < p.nvox; it += warps_total) {
+        // Traversal order: z-slices (all resident warps sweep the volume slice by slice).  Voxels that share a
+        // pixel lie along one camera ray, and rays of roughly level cameras stay within a few z-slices, so
+        // their repeated gathers of that pixel's row fall inside the L2 residency window (DESIGN.md "K_A").
+        int vx, vy, vz;
+        if (p.order == 0) {
+            vz = it / nxy;
+            const int rem = it - vz * nxy;
+            vx = rem / p.g.ny;
+            vy = rem - vx * p.g.ny;
+        } else {
+            vz = it % p.g.nz;
+            const int vxy = it / p.g.nz;
+            vy = vxy % p.g.ny;
+            vx = vxy / p.g.ny;
         }
-        const unsigned ballot = __ballot_sync(0xffffffffu, off >= 0);
-        unsigned bits = (ballot >> (grp * G)) & kGroupMask;
-        cnt += __popc(bits);
-        while (__any_sync(0xffffffffu, bits != 0u)) {
-            const T *src[kUnroll];
+        // voxel order of datasets/tsdf.py:24-29: flat = (x*ny + y)*nz + z
+        const int vox = (vx * p.g.ny + vy) * p.g.nz + vz;
+        const float wx = world_coord(vx, p.g.vs, p.g.ox);
+        const float wy = world_coord(vy, p.g.vs, p.g.oy);
+        const float wz = world_coord(vz, p.g.vs, p.g.oz);
+
+        float acc[VPL][E];
+        int cnt = 0;
+        if (p.flags & CNRMA_AGG_ACCUMULATE) {
+            cnt = (p.flags & CNRMA_AGG_COUNT_F32) ? (int)reinterpret_cast<const float *>(p.count)[vox] : p.count[vox];
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const int j = bits ? (__ffs(bits) - 1) : 0;
-                const int o = __shfl_sync(0xffffffffu, off, grp * G + j);
-                src[u] = bits ? (sView[v0 + j] + o + c0) : nullptr;
-                bits &= bits - 1u;
+            for (int k = 0; k < VPL; ++k)
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int c = c0 + (lane + 32 * k) * E + e;
+                    acc[k][e] = (lane + 32 * k < nvec) ? p.volume[(int64_t)vox * p.vsv + (int64_t)c * p.vsc] : 0.0f;
+                }
+        } else {
+#pragma unroll
+            for (int k = 0; k < VPL; ++k)
+#pragma unroll
+                for (int e = 0; e < E; ++e) acc[k][e] = 0.0f;
+        }
+
+        int filled = 0;   // rows issued into the buffer and not yet added (warp-uniform)
+        // adds the buffered rows in slot order (== view order) once their bytes have landed
+        auto drain = [&]() {
+            if (lane == 0) mbar_arrive(bar);
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+            for (int r = 0; r < filled; ++r) {
+#pragma unroll
+                for (int k = 0; k < VPL; ++k) {
+                    const int j = lane + 32 * k;
+                    if (j < nvec) {
+                        const V16 val = V16::load_shared(rowbuf + (size_t)r * p.chunk_bytes + (j << 4));
+#pragma unroll
+                        for (int e = 0; e < E; ++e) acc[k][e] = __fadd_rn(acc[k][e], val.v[e]);
+                    }
+                }
             }
-            V16 val[kUnroll][VPL];
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u)
-                if (src[u] != nullptr) {
-#pragma unroll
-                    for (int k = 0; k < VPL; ++k) val[u][k] = V16::load(src[u] + k * G * E);
-                }
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u)
-                if (src[u] != nullptr) {
-#pragma unroll
-                    for (int k = 0; k < VPL; ++k)
-#pragma unroll
-                        for (int e = 0; e < E; ++e) acc[k][e] = __fadd_rn(acc[k][e], val[u][k].v[e]);
-                }
-        }
-    }
+            filled = 0;
+            __syncwarp();   // all lanes are done reading before the slots are overwritten
+        };
 
-    if (!vox_ok) return;
-    if (p.flags & CNRMA_AGG_MEAN) {
-        const float n = (float)cnt;   // rm.py:251: fp32 sum / int64 count -> true division by float(count)
+        for (int v0 = 0; v0 < p.V; v0 += 32) {
+            const int view = v0 + lane;
+            int64_t off = -1;
+            if (view < p.V) {
+                int px, py;
+                if (project_voxel(sP + view, Vpad, wx, wy, wz, p.H, p.W, px, py))
+                    off = (py * p.stride_y + px * p.stride_x) * esz;
+            }
+            const unsigned bits = __ballot_sync(0xffffffffu, off >= 0);
+            const int n = __popc(bits);
+            const int rank = __popc(bits & ((1u << lane) - 1u));
+            cnt += n;
+            int done = 0;   // visible views of this round already issued
+            while (done < n) {
+                if (filled == p.rows_cap) drain();
+                const int take = min(p.rows_cap - filled, n - done);
+                if (lane == 0) mbar_expect_tx(bar, (uint32_t)(take * p.chunk_bytes));
+                __syncwarp();
+                if (off >= 0 && rank >= done && rank < done + take)
+                    bulk_g2s(buf0 + (uint32_t)((filled + rank - done) * p.chunk_bytes), sView[view] + off,
+                             (uint32_t)p.chunk_bytes, bar);
+                filled += take;
+                done += take;
+            }
+        }
+        if (filled > 0) drain();
+
+        if (p.flags & CNRMA_AGG_MEAN) {
+            // rm.py:251: fp32 sum / int64 count -> IEEE division by float(count); 0 where count == 0
+            const float n = (float)cnt;
+            const float y = __frcp_rn(n);
 #pragma unroll
-        for (int k = 0; k < VPL; ++k)
+            for (int k = 0; k < VPL; ++k)
 #pragma unroll
-            for (int e = 0; e < E; ++e) acc[k][e] = (cnt > 0) ? __fdiv_rn(acc[k][e], n) : 0.0f;
-    }
-    if (p.vec_store) {
+                for (int e = 0; e < E; ++e) acc[k][e] = (cnt > 0) ? div_by_count(acc[k][e], n, y) : 0.0f;
+        }
 #pragma unroll
         for (int k = 0; k < VPL; ++k) {
-            float *dst = p.volume + (int64_t)vox * p.vsv + (c0 + k * G * E);
+            const int j = lane + 32 * k;
+            if (j < nvec) {
+                const int c = c0 + j * E;
+                if (p.vec_store) {
+                    float *dst = p.volume + (int64_t)vox * p.vsv + c;
 #pragma unroll
-            for (int e = 0; e < E; e += 4)
-                __stcs(reinterpret_cast<float4 *>(dst + e),
-                       make_float4(acc[k][e], acc[k][e + 1], acc[k][e + 2], acc[k][e + 3]));
+                    for (int e = 0; e < E; e += 4)
+                        __stcs(reinterpret_cast<float4 *>(dst + e),
+                               make_float4(acc[k][e], acc[k][e + 1], acc[k][e + 2], acc[k][e + 3]));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) p.volume[(int64_t)vox * p.vsv + (int64_t)(c + e) * p.vsc] = acc[k][e];
+                }
+            }
         }
-    } else {
-#pragma unroll
-        for (int k = 0; k < VPL; ++k)
-#pragma unroll
-            for (int e = 0; e < E; ++e)
-                p.volume[(int64_t)vox * p.vsv + (int64_t)(c0 + k * G * E + e) * p.vsc] = acc[k][e];
-    }
-    if (lig == 0 && blockIdx.y == 0 && p.write_count) {
-        if (p.flags & CNRMA_AGG_COUNT_F32) reinterpret_cast<float *>(p.count)[vox] = (float)cnt;
-        else p.count[vox] = cnt;
-        if (p.valid != nullptr) p.valid[vox] = (uint8_t)(cnt > 0);
+        if (lane == 0 && blockIdx.y == 0 && p.write_count) {
+            if (p.flags & CNRMA_AGG_COUNT_F32) reinterpret_cast<float *>(p.count)[vox] = (float)cnt;
+            else p.count[vox] = cnt;
+            if (p.valid != nullptr) p.valid[vox] = (uint8_t)(cnt > 0);
+        }
     }
 }
 
 // ---- launch ------------------------------------------------------------------------------------
 
-template <int G, int VPL, typename T>
+// Largest divisor of `row_bytes` that is a multiple of 16 and <= kMaxChunkBytes.
+static int plan_chunk_bytes(int row_bytes, int max_chunk_bytes) {
+    const int units = row_bytes / 16;
+    int best = 1;
+    for (int d = 1; d <= units; ++d)
+        if (units % d == 0 && d * 16 <= max_chunk_bytes) best = d;
+    return best * 16;
+}
+
+template <int VPL, typename T>
 static cudaError_t launch_agg(const AggParams &p, int chunks, cudaStream_t stream) {
-    constexpr int kVoxPerCta = (kAggThreads / kWarp) * (kWarp / G);
-    const dim3 grid((p.nvox + kVoxPerCta - 1) / kVoxPerCta, chunks);
     const int Vpad = p.V | 1;
-    const size_t smem = sizeof(void *) * p.V + sizeof(float) * 12 * Vpad;
-    aggregate_views_kernel<G, VPL, T><<<grid, kAggThreads, smem, stream>>>(p);
+    const size_t head = (8 * (kAggThreads / kWarp) + sizeof(void *) * p.V + sizeof(float) * 12 * Vpad + 127) & ~(size_t)127;
+    const size_t smem = head + (size_t)(kAggThreads / kWarp) * p.rows_cap * p.chunk_bytes;
+    auto kernel = aggregate_views_kernel<VPL, T>;
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kAggThreads, smem);
+    if (err != cudaSuccess) return err;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    const int needed = (p.nvox + (kAggThreads / kWarp) - 1) / (kAggThreads / kWarp);
+    const int persistent = sms * per_sm;
+    const dim3 grid(needed < persistent ? needed : persistent, chunks);
+    kernel<<<grid, kAggThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
-template <int G, typename T>
-static cudaError_t launch_agg_vpl(const AggParams &p, int vpl, int chunks, cudaStream_t stream) {
-    switch (vpl) {
-        case 1: return launch_agg<G, 1, T>(p, chunks, stream);
-        case 2: return launch_agg<G, 2, T>(p, chunks, stream);
-        case 3: return launch_agg<G, 3, T>(p, chunks, stream);
-        case 4: return launch_agg<G, 4, T>(p, chunks, stream);
-    }
-    return cudaErrorInvalidValue;
-}
-
-template <typename T>
-static cudaError_t launch_agg_g(const AggParams &p, int g, int vpl, int chunks, cudaStream_t stream) {
-    switch (g) {
-        case 1: return launch_agg_vpl<1, T>(p, vpl, chunks, stream);
-        case 2: return launch_agg_vpl<2, T>(p, vpl, chunks, stream);
-        case 4: return launch_agg_vpl<4, T>(p, vpl, chunks, stream);
-        case 8: return launch_agg_vpl<8, T>(p, vpl, chunks, stream);
-        case 16: return launch_agg_vpl<16, T>(p, vpl, chunks, stream);
-        case 32: return launch_agg_vpl<32, T>(p, vpl, chunks, stream);
-    }
-    return cudaErrorInvalidValue;
-}
-
-// Chooses lanes-per-voxel G, vectors-per-lane VPL and the number of channel chunks for `nvec` 16-byte
-// vectors per feature row.  `max_chunk_vecs` (0 = no limit) caps G*VPL, which trades redundant
-// projection work for a smaller per-pass L2 working set.
-static void plan_agg(int nvec, int max_chunk_vecs, int &g, int &vpl, int &chunks) {
-    g = 1;
-    while (g < 32 && (nvec % (g * 2)) == 0) g *= 2;
-    if (max_chunk_vecs > 0)
-        while (g > 1 && g > max_chunk_vecs) g /= 2;
-    const int q = nvec / g;
-    vpl = 1;
-    for (int d = 4; d >= 1; --d)
-        if (q % d == 0 && (max_chunk_vecs <= 0 || g * d <= max_chunk_vecs || d == 1)) {
-            vpl = d;
-            break;
-        }
-    chunks = q / vpl;
-}
-
-static cudaError_t run_aggregate(const AggParams &p_in, int dtype, int max_chunk_vecs, cudaStream_t stream) {
-    const int e = (dtype == CNRMA_BF16) ? 8 : 4;
-    int g, vpl, chunks;
-    plan_agg(p_in.C / e, max_chunk_vecs, g, vpl, chunks);
+static cudaError_t run_aggregate(const AggParams &p_in, int dtype, int max_chunk_bytes, cudaStream_t stream) {
+    const int esz = (dtype == CNRMA_BF16) ? 2 : 4;
     AggParams p = p_in;
+    if (max_chunk_bytes <= 0 || max_chunk_bytes > kMaxChunkBytes) max_chunk_bytes = kMaxChunkBytes;
+    p.chunk_bytes = plan_chunk_bytes(p.C * esz, max_chunk_bytes);
+    const int chunks = (p.C * esz) / p.chunk_bytes;
+    int warp_buffer = kWarpBufferBytes;
+    if (const char *env = std::getenv("CNRMA_AGG_WARP_BUFFER")) warp_buffer = std::atoi(env);   // tuning aid
+    p.rows_cap = warp_buffer / p.chunk_bytes;
+    if (p.rows_cap < 1) p.rows_cap = 1;
+    p.order = 0;
+    if (const char *env = std::getenv("CNRMA_AGG_ORDER")) p.order = std::atoi(env);   // tuning aid
+    if (p.rows_cap > 32) p.rows_cap = 32;
+    const int vpl = (p.chunk_bytes / 16 + 31) / 32;
+    auto launch = [&](const AggParams &q, int nchunks) -> cudaError_t {
+        if (dtype == CNRMA_BF16)
+            return vpl == 1 ? launch_agg<1, __nv_bfloat16>(q, nchunks, stream) : launch_agg<2, __nv_bfloat16>(q, nchunks, stream);
+        return vpl == 1 ? launch_agg<1, float>(q, nchunks, stream) : launch_agg<2, float>(q, nchunks, stream);
+    };
     p.chunk_base = 0;
     p.write_count = 1;
-    if (!(p.flags & CNRMA_AGG_ACCUMULATE) || chunks == 1) {
-        if (dtype == CNRMA_BF16) return launch_agg_g<__nv_bfloat16>(p, g, vpl, chunks, stream);
-        return launch_agg_g<float>(p, g, vpl, chunks, stream);
-    }
+    if (!(p.flags & CNRMA_AGG_ACCUMULATE) || chunks == 1) return launch(p, chunks);
     // Accumulating launches read the previous count; with several channel chunks in one grid the chunk
     // that rewrites it would race with the others, so the chunks go out one launch at a time (stream
     // ordered) and only the last one stores the new count.
     for (int c = 0; c < chunks; ++c) {
         p.chunk_base = c;
         p.write_count = (c == chunks - 1);
-        const cudaError_t err = (dtype == CNRMA_BF16) ? launch_agg_g<__nv_bfloat16>(p, g, vpl, 1, stream)
-                                                       : launch_agg_g<float>(p, g, vpl, 1, stream);
+        const cudaError_t err = launch(p, 1);
         if (err != cudaSuccess) return err;
     }
     return cudaSuccess;
@@ -243,7 +319,7 @@ static cudaError_t run_aggregate(const AggParams &p_in, int dtype, int max_chunk
 // Views [v0, v0 + nv) of `f` in one launch (nv <= kMaxViewsPerLaunch).
 cudaError_t run_aggregate_views(const GridDev &g, const cnrma_features &f, int v0, int nv, const float *proj,
                                 int64_t proj_stride, float stride, uint32_t flags, float *volume, int64_t vsv,
-                                int64_t vsc, int32_t *count, uint8_t *valid, int max_chunk_vecs, cudaStream_t stream) {
+                                int64_t vsc, int32_t *count, uint8_t *valid, int max_chunk_bytes, cudaStream_t stream) {
     AggParams p;
     p.g = g;
     p.V = nv;
@@ -266,7 +342,40 @@ cudaError_t run_aggregate_views(const GridDev &g, const cnrma_features &f, int v
     p.chunk_base = 0;
     p.write_count = 1;
     for (int i = 0; i < nv; ++i) p.views[i] = f.view_ptrs_host[v0 + i];
-    return run_aggregate(p, f.dtype, max_chunk_vecs, stream);
+    p.chunk_bytes = 0;
+    p.rows_cap = 0;
+    return run_aggregate(p, f.dtype, max_chunk_bytes, stream);
+}
+
+// ---- exhaustive check of div_by_count ---------------------------------------------------------------
+// For every count n in [1, max_n] and every fp32 significand (one full binade, both signs, plus two far
+// binades: scaling by a power of two is exact, so one binade stands for all normal values inside the guarded
+// range), compares div_by_count against __fdiv_rn.  Returns the number of mismatches (must be 0).
+__global__ void __launch_bounds__(256) selftest_count_division_kernel(int max_n, unsigned long long *mismatches) {
+    const uint32_t sig = blockIdx.x * blockDim.x + threadIdx.x;   // 2^23 significands
+    if (sig >= (1u << 23)) return;
+    const int n_lo = blockIdx.y * 16 + 1;
+    unsigned long long bad = 0;
+    for (int ni = n_lo; ni < n_lo + 16 && ni <= max_n; ++ni) {
+        const float n = (float)ni;
+        const float y = __frcp_rn(n);
+        const uint32_t exps[3] = {127u, 127u - 40u, 127u + 40u};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float a = __uint_as_float((exps[k] << 23) | sig);
+            bad += (__float_as_uint(div_by_count(a, n, y)) != __float_as_uint(__fdiv_rn(a, n)));
+            bad += (__float_as_uint(div_by_count(-a, n, y)) != __float_as_uint(__fdiv_rn(-a, n)));
+        }
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+cudaError_t run_selftest_count_division(int max_n, unsigned long long *mismatches, cudaStream_t stream) {
+    cudaError_t err = cudaMemsetAsync(mismatches, 0, sizeof(unsigned long long), stream);
+    if (err != cudaSuccess) return err;
+    const dim3 grid((1u << 23) / 256, (max_n + 15) / 16);
+    selftest_count_division_kernel<<<grid, 256, 0, stream>>>(max_n, mismatches);
+    return cudaGetLastError();
 }
 
 // ---- per-view indices and masks (parity surface of rm.py:47-58) ---------------------------------

@@ -59,23 +59,49 @@ struct MarchParams {
     cnrma_rma_result *result;
 };
 
+// Per-ray constants of the position -> voxel id mapping.
+struct VoxelMap {
+    float inv_vs;      // RN(1 / voxel_size)
+    bool zero_origin;  // origin == (0,0,0): `places - origin` is the identity and is skipped
+};
+
+// round((p - origin) / voxel_size) for one coordinate (rm.py:730: sub, true division, half-to-even).
+// The quotient is only needed rounded to an integer, so the IEEE division is replaced by a multiplication with
+// the rounded reciprocal whenever that provably cannot change the result: q_fast = RN(rel * RN(1/vs)) is
+// within |q| * 2^-23 of the exact quotient, hence rint(q_fast) == rint(RN(rel / vs)) unless q_fast lies within
+// |q| * 2^-22 of a half-integer -- in which case (about one sample in 10^4) the division is done for real.
+__device__ __forceinline__ float voxel_coord(float p, float o, float vs, const VoxelMap &m) {
+    const float rel = m.zero_origin ? p : __fsub_rn(p, o);
+    const float q = __fmul_rn(rel, m.inv_vs);
+    float r = rintf(q);
+    const float frac = __fsub_rn(q, r);
+    const float safe = __fmaf_rn(fabsf(q), -2.384185791015625e-07f, 0.5f);   // 0.5 - |q| * 2^-22
+    if (!(fabsf(frac) < safe)) r = rintf(__fdiv_rn(rel, vs));   // also taken for NaN / huge q
+    return r;
+}
+
 // One sample of a ray (rm.py:729-733): position -> rounded voxel id; returns the flat id or -1 outside the grid.
-__device__ __forceinline__ int sample_voxel(const GridDev &g, const float o[3], const float d[3], float t) {
-    const float px = __fadd_rn(o[0], __fmul_rn(d[0], t));
-    const float py = __fadd_rn(o[1], __fmul_rn(d[1], t));
-    const float pz = __fadd_rn(o[2], __fmul_rn(d[2], t));
-    // ((places - origin) / voxel_size).round(): sub, true division, half-to-even (rm.py:730)
-    const float qx = rintf(__fdiv_rn(__fsub_rn(px, g.ox), g.vs));
-    const float qy = rintf(__fdiv_rn(__fsub_rn(py, g.oy), g.vs));
-    const float qz = rintf(__fdiv_rn(__fsub_rn(pz, g.oz), g.vs));
+__device__ __forceinline__ int sample_voxel(const GridDev &g, const VoxelMap &m, const float o[3], const float d[3],
+                                            float t) {
+    const float qx = voxel_coord(__fadd_rn(o[0], __fmul_rn(d[0], t)), g.ox, g.vs, m);
+    const float qy = voxel_coord(__fadd_rn(o[1], __fmul_rn(d[1], t)), g.oy, g.vs, m);
+    const float qz = voxel_coord(__fadd_rn(o[2], __fmul_rn(d[2], t)), g.oz, g.vs, m);
+    // integer-valued floats (or NaN / inf, which fail every comparison like the reference's INT64_MIN)
     const bool inb = (qx >= 0.0f) && (qx < (float)g.nx) && (qy >= 0.0f) && (qy < (float)g.ny) && (qz >= 0.0f) &&
                      (qz < (float)g.nz);
     return inb ? (((int)qx * g.ny + (int)qy) * g.nz + (int)qz) : -1;
 }
 
+__device__ __forceinline__ VoxelMap make_voxel_map(const GridDev &g) {
+    VoxelMap m;
+    m.inv_vs = __frcp_rn(g.vs);
+    m.zero_origin = (g.ox == 0.0f) && (g.oy == 0.0f) && (g.oz == 0.0f);
+    return m;
+}
+
 __device__ __forceinline__ float sigmoid_neg(float tv) {
-    // torch.sigmoid(-tsdf) = 1 / (1 + exp(tsdf)) (rm.py:757)
-    return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(tv)));
+    // torch.sigmoid(-tsdf) = 1 / (1 + exp(tsdf)) (rm.py:757); the correctly rounded reciprocal is the IEEE quotient
+    return __frcp_rn(__fadd_rn(1.0f, expf(tv)));
 }
 
 template <int BLOCK>
@@ -109,6 +135,9 @@ __device__ __forceinline__ void block_totals(int kept, double wsum, int32_t *blk
 //   s_i = sigmoid(-tsdf_i); alpha_i = max((s_i - s_{i+1}) / s_i, 0) with s_N := s_{N-1};
 //   T_i = prod_{j<i} (1 - alpha_j) (sequential product, like torch.cumprod on CPU); w_i = T_i * alpha_i;
 //   keep_i = in-bounds_i & (w_i >= thr).
+// Consecutive samples that read the same TSDF value (same voxel, or neighbouring voxels of equal value such as
+// free space) have alpha == 0 exactly: the transmittance is unchanged and, for thr > 0, nothing is kept, so the
+// exp / divisions are only evaluated where the TSDF value changes.
 __global__ void __launch_bounds__(kRayThreads) march_neus_kernel(const __grid_constant__ MarchParams p) {
     const int64_t ray = (int64_t)blockIdx.x * kRayThreads + threadIdx.x;
     int kept = 0;
@@ -119,25 +148,25 @@ __global__ void __launch_bounds__(kRayThreads) march_neus_kernel(const __grid_co
         const int pix = (int)(ray % hw);
         float o[3], d[3];
         ray_of_pixel(p.pinv + 16 * view, pix % p.W, pix / p.W, o, d);
+        const VoxelMap vm = make_voxel_map(p.g);
+        const bool keep_zero = !(p.thr > 0.0f);   // thr <= 0 (or NaN): zero weights pass `w >= thr` too
 
-        const float s_out = sigmoid_neg(1.0f);   // samples outside the grid read tsdf = 1.0 (rm.py:744)
         float T = 1.0f;
-        float s_cur = 0.0f;
+        float tv_cur = 1.0f, s_cur = 0.0f;   // TSDF value / sigmoid of the current sample (set at i == 0)
         int vox_cur = -1;
         bool entered = false;
         int overflow = 0;
         for (int i = 0; i <= p.N; ++i) {
-            float s_next;
-            int vox_next;
+            int vox_next = -1;
+            float tv_next = tv_cur;   // i == N: last sample repeated (rm.py:758)
             if (i < p.N) {
-                vox_next = sample_voxel(p.g, o, d, __fmul_rn((float)i, p.t_one));
-                if (i > 0 && vox_next == vox_cur) s_next = s_cur;   // same voxel -> same tsdf -> same sigmoid
-                else s_next = (vox_next >= 0) ? sigmoid_neg(__ldg(p.tsdf + vox_next)) : s_out;
-            } else {
-                vox_next = -1;
-                s_next = s_cur;   // last sample repeated (rm.py:758)
+                vox_next = sample_voxel(p.g, vm, o, d, __fmul_rn((float)i, p.t_one));
+                // samples outside the grid read tsdf = 1.0 (rm.py:744); same voxel -> same value
+                if (i == 0 || vox_next != vox_cur) tv_next = (vox_next >= 0) ? __ldg(p.tsdf + vox_next) : 1.0f;
             }
-            if (i > 0) {
+            float s_next = s_cur;
+            if (i == 0 || tv_next != tv_cur) s_next = sigmoid_neg(tv_next);
+            if (i > 0 && (s_next != s_cur || keep_zero)) {
                 float a = __fdiv_rn(__fsub_rn(s_cur, s_next), s_cur);
                 a = (a < 0.0f) ? 0.0f : a;   // clamp(min=0), NaN-propagating like torch
                 const float w = __fmul_rn(T, a);
@@ -152,13 +181,14 @@ __global__ void __launch_bounds__(kRayThreads) march_neus_kernel(const __grid_co
                     }
                 }
                 T = __fmul_rn(T, __fsub_rn(1.0f, a));
-                // exact early exits: (a) every later weight is <= T < thr; (b) the grid is convex and the
-                // rounded sample ids are monotone along the ray, so once left it is never re-entered and
-                // samples outside are never kept.
+                // exact early exit: every later weight is <= T < thr
                 if (p.thr > 0.0f && T < p.thr) break;
-                if (entered && vox_next < 0) break;
             }
+            // exact early exit: the grid is convex and the rounded sample ids are monotone along the ray, so once
+            // left it is never re-entered, and samples outside are never kept
+            if (entered && vox_next < 0) break;
             entered = entered || (vox_next >= 0);
+            tv_cur = tv_next;
             s_cur = s_next;
             vox_cur = vox_next;
         }
@@ -180,11 +210,12 @@ __global__ void __launch_bounds__(kRayThreads) march_depth_kernel(const __grid_c
         const int pix = (int)(ray % hw);
         float o[3], d[3];
         ray_of_pixel(p.pinv + 16 * view, pix % p.W, pix / p.W, o, d);
+        const VoxelMap vm = make_voxel_map(p.g);
         int best = -1;
         float tv_cur = 1.0f;
         int vox_cur = -1;
         for (int i = 0; i < p.N; ++i) {
-            const int vox = sample_voxel(p.g, o, d, __fmul_rn((float)i, p.t_one));
+            const int vox = sample_voxel(p.g, vm, o, d, __fmul_rn((float)i, p.t_one));
             const float tv = (i > 0 && vox == vox_cur) ? tv_cur : ((vox >= 0) ? __ldg(p.tsdf + vox) : 1.0f);
             if (i > 0 && __fmul_rn(tv_cur, tv) <= 0.0f) {
                 best = i - 1;

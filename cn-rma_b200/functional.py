@@ -70,12 +70,15 @@ class _FeatureStack:
             raise CnrmaError(f"channels must be a multiple of {e} for {self.dtype}")
         strides = {f.stride()[1:] for f in self.views}
         sc, sy, sx = next(iter(strides))
-        aligned = all(f[b].data_ptr() % 16 == 0 for f in self.views for b in range(self.B))
+        esz = f0.element_size()
+        aligned = all(f.data_ptr() % 16 == 0 and (f.stride(0) * esz) % 16 == 0 for f in self.views)
         cl = len(strides) == 1 and sc == 1 and (not need_vector_layout or (sx % e == 0 and sy % e == 0 and aligned))
         if not cl:
             self.views = self._to_channels_last()
         self.sc, self.sy, self.sx = self.views[0].stride()[1:]
         self.converted = not cl
+        self._base = [f.data_ptr() for f in self.views]
+        self._bstride = [f.stride(0) * esz for f in self.views]
 
     def _to_channels_last(self):
         lib = _lib.load()
@@ -92,7 +95,7 @@ class _FeatureStack:
 
     def descriptor(self, b, v0=0, nv=None):
         nv = self.V - v0 if nv is None else nv
-        ptrs = (C.c_void_p * nv)(*[self.views[v][b].data_ptr() for v in range(v0, v0 + nv)])
+        ptrs = (C.c_void_p * nv)(*[self._base[v] + b * self._bstride[v] for v in range(v0, v0 + nv)])
         desc = _lib.Features(nv, self.C, self.H, self.W, _DTYPES[self.dtype], self.sc, self.sy, self.sx,
                              C.cast(ptrs, C.POINTER(C.c_void_p)))
         desc._keepalive = ptrs
@@ -218,12 +221,24 @@ def backproject(voxel_dim, voxel_size, origin, projection, features):
 # ----------------------------------------------------------------------------------------------------
 
 def invert_projections(projections_scaled):
-    """rm.py:96-102: inverse of [P; 0 0 0 1] per view, with the reference's own call (torch.inverse on one
-    4x4 fp32 matrix) on the host, so the ray parameters are bit-identical to the CPU reference.
-    projections_scaled [V,3,4] (any device) -> [V,4,4] CPU fp32."""
+    """rm.py:96-102: inverse of [P; 0 0 0 1] per view with the reference's own LAPACK call (torch.inverse, CPU,
+    fp32) on the host, so the ray parameters are bit-identical to the CPU reference.  The batched call runs the
+    same per-matrix getrf/getri as the reference's one-matrix calls (bit-identical, checked in the tests); it is
+    issued single-threaded because OpenMP fan-out over fifty 4x4 matrices costs milliseconds.
+    projections_scaled [V,3,4] (any device) -> [V,4,4] CPU fp32 (pinned when CUDA is available)."""
     P = projections_scaled.detach().to("cpu", torch.float32)
-    last = torch.tensor([[0.0, 0.0, 0.0, 1.0]])
-    return torch.stack([torch.inverse(torch.cat((P[v], last), dim=0)) for v in range(P.shape[0])], dim=0)
+    V = P.shape[0]
+    p4 = torch.zeros((V, 4, 4), dtype=torch.float32)
+    p4[:, :3, :] = P
+    p4[:, 3, 3] = 1.0
+    out = torch.empty((V, 4, 4), dtype=torch.float32, pin_memory=torch.cuda.is_available())
+    threads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        torch.inverse(p4, out=out)
+    finally:
+        torch.set_num_threads(threads)
+    return out
 
 
 def scale_projections(projections, stride):
@@ -255,7 +270,13 @@ class _March:
     pass
 
 
-def _march(fs, b, P_scaled_b, tsdf_b, grid, voxel_dim, voxel_size, grids, mode, threshold, depth_points):
+def prepare_pinv(projections_scaled_b, device):
+    """Host half of get_ray_parameter (rm.py:96-102) for one batch element: [V,3,4] scaled projections ->
+    device tensor [V,4,4].  Separate so that callers can do it before queueing unrelated GPU work."""
+    return invert_projections(projections_scaled_b).to(device, non_blocking=True)
+
+
+def _march(fs, b, P_scaled_b, tsdf_b, grid, voxel_dim, voxel_size, grids, mode, threshold, depth_points, pinv=None):
     lib = _lib.load()
     device = fs.device
     m = _March()
@@ -263,14 +284,15 @@ def _march(fs, b, P_scaled_b, tsdf_b, grid, voxel_dim, voxel_size, grids, mode, 
     m.threshold = float(threshold if threshold is not None else 0.0)
     m.depth_points = int(depth_points if depth_points is not None else 0)
     m.grids = int(grids)
-    m.pinv = invert_projections(P_scaled_b).to(device)
+    m.pinv = pinv if pinv is not None else prepare_pinv(P_scaled_b, device)
     m.t_one = lib.cnrma_t_one(C.byref(grid), float(voxel_size), m.grids)
     nbytes = C.c_size_t(0)
     _lib.check(lib.cnrma_rma_workspace_bytes(fs.V, fs.H, fs.W, m.grids, m.mode, m.threshold, m.depth_points,
                                              C.byref(nbytes)), "cnrma_rma_workspace_bytes")
     m.workspace = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
     m.result = torch.empty(C.sizeof(_lib.RmaResult), dtype=torch.uint8, device=device)
-    tsdf_b = tsdf_b.detach().to(device=device, dtype=torch.float32).contiguous()
+    if tsdf_b.dtype != torch.float32 or not tsdf_b.is_contiguous() or tsdf_b.device != device:
+        tsdf_b = tsdf_b.detach().to(device=device, dtype=torch.float32).contiguous()
     if tuple(tsdf_b.shape) != tuple(int(v) for v in voxel_dim):
         raise ValueError("tsdf must be [B,1,nx,ny,nz]")
     m.tsdf = tsdf_b

@@ -112,6 +112,13 @@ int cnrma_aggregate_views(const cnrma_grid *grid, const cnrma_features *features
                           int64_t vol_stride_voxel, int64_t vol_stride_channel, int32_t *count, uint8_t *valid,
                           void *stream);
 
+/* Proof obligation of the fused mean (rm.py:251 `volume / valid`): the kernel divides by the view count with
+ * one correctly rounded reciprocal and a Markstein correction instead of a generic division.  This entry
+ * point checks that shortcut against IEEE division for every count in [1, max_n] and every fp32 significand
+ * (both signs, three binades) and writes the number of mismatches -- which must be 0 -- to *mismatches
+ * (device uint64). */
+int cnrma_selftest_count_division(int max_n, uint64_t *mismatches, void *stream);
+
 /* Layout helper for reference-layout (NCHW) feature maps: src [V][C,H,W] with the given strides ->
  * dst channels-last [V,H,W,C] contiguous, same dtype.  One read + one write of the features. */
 int cnrma_to_channels_last(const cnrma_features *src, void *dst, void *stream);

@@ -79,8 +79,9 @@ def test_scale_and_invert_projections_follow_reference_ops():
     want[:, :2, :] = want[:, :2, :] / 4                         # rm.py:238-239
     assert torch.equal(ps, want)
     inv = cn.invert_projections(ps)
-    p4 = torch.cat((ps[1], torch.tensor([[0.0, 0, 0, 1]])), 0)
-    assert torch.equal(inv[1], torch.inverse(p4))               # rm.py:96-102
+    for v in range(ps.shape[0]):                                # one torch.inverse per matrix, rm.py:96-102
+        p4 = torch.cat((ps[v], torch.tensor([[0.0, 0, 0, 1]])), 0)
+        assert torch.equal(inv[v], torch.inverse(p4))
 
 
 def test_shards():

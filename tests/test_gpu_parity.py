@@ -263,6 +263,9 @@ def test_oracle_points(cn, scene, mode, kw):
                                                     ray_marching_type=mode,
                                                     neus_threshold=kw.get("threshold", 0.05),
                                                     depth_points=kw.get("depth_points"))
+    if ref is None:               # nothing kept anywhere (e.g. a high threshold on a coarse grid)
+        assert pts.shape[0] == 0
+        return
     assert pts.shape == ref.shape
     assert np.array_equal(pts[:, :3].view(np.uint32), ref[:, :3].view(np.uint32))
     assert_rel(pts[:, 3:], ref[:, 3:], FP32_REL, what=f"{mode} points")
@@ -277,10 +280,20 @@ def test_oracle_dense_rma(cn, scene):
                                                      sc.voxel_size, sc.origin, sc.stride, grids=sc.grids,
                                                      normalize=False)
     osum, otot = oracle.dense_rma(rows, sc.voxel_dim, sc.voxel_size, sc.origin)
-    assert_rel(wtot[0, 0].cpu().numpy(), otot, FP32_REL, floor=1e-3, what="wtot")
-    # sums of signed terms: tolerance relative to the per-voxel weight total (atomics reorder the adds)
-    err = np.abs(wsum[0].cpu().numpy() - osum) / np.maximum(otot[None] * 4.0, 1e-3)
-    assert err.max() <= FP32_REL
+    # fp32 atomics accumulate in arbitrary order (the oracle sums in double): a voxel that receives n terms
+    # may be off by n * 2^-24 of its total -- voxels next to a camera collect one sample from every ray of
+    # the view.  Tolerance = north_star's 1e-5 plus that accumulation bound.
+    ids = np.rint((rows[:, :3] - sc.origin[None]) / np.float32(sc.voxel_size)).astype(np.int64)
+    nx, ny, nz = sc.voxel_dim
+    inb = np.all((ids >= 0) & (ids < np.array([nx, ny, nz])), axis=1)
+    flat = (ids[inb, 0] * ny + ids[inb, 1]) * nz + ids[inb, 2]
+    n_terms = np.bincount(flat, minlength=nx * ny * nz).reshape(nx, ny, nz)
+    tol = FP32_REL + n_terms * 2.0 ** -24
+    gt, gs = wtot[0, 0].cpu().numpy(), wsum[0].cpu().numpy()
+    assert np.all(np.abs(gt - otot) <= tol * np.maximum(otot, 1e-3)), "wtot"
+    mag = np.zeros_like(otot, dtype=np.float64)          # sum of |w * feat| bounds the rounding of signed sums
+    np.add.at(mag.reshape(-1), flat, (rows[inb, 3:4] * np.abs(rows[inb, 4:])).max(axis=1))
+    assert np.all(np.abs(gs - osum) <= tol[None] * np.maximum(mag[None], 1e-3)), "wsum"
 
 
 def test_bf16_features(cn, scene):
@@ -315,3 +328,13 @@ def test_errors_are_loud(cn):
         cn.rma_points(p, f, t, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride, mode="neus")     # no threshold
     with pytest.raises(cn.CnrmaError):
         cn.aggregate_views(p, f.double(), sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
+
+
+def test_count_division_shortcut_is_ieee_exact(cn):
+    """The mean's divide-by-count shortcut == IEEE division for every count 1..512 and every significand."""
+    import ctypes as C
+    lib = cn.load()
+    out = torch.zeros(1, dtype=torch.int64, device="cuda")
+    st = lib.cnrma_selftest_count_division(512, C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert st == 0
+    assert int(out.item()) == 0
