@@ -203,7 +203,8 @@ def main():
     feats = cn.synthetic.device_features(sc, dev, channels_last=True)           # [V,1,C,H,W] logical
     if sc.meta.get("dtype") == "bf16":
         feats = feats.to(torch.bfloat16)
-    proj = torch.from_numpy(sc.projections).to(dev).unsqueeze(1)
+    proj_host = torch.from_numpy(sc.projections).unsqueeze(1)     # cameras originate on the host (dataloader);
+    proj = proj_host.to(dev)                                      # Stage A reads the device copy
     tsdf = torch.from_numpy(sc.tsdf).to(dev)[None, None]
     V, C, H, W = sc.views, sc.channels, sc.height, sc.width
     esz = feats.element_size()
@@ -216,7 +217,7 @@ def main():
     def step(ev=None):
         # host half of the ray set-up first (4x4 LAPACK inverses, rm.py:96-102), so that it overlaps with the
         # GPU work already queued instead of delaying the march launch
-        pinv = F.prepare_pinv(F.scale_projections(proj, sc.stride)[:, 0], dev) if args.stage in ("both", "b") else None
+        pinv = F.prepare_pinv(F.scale_projections(proj_host, sc.stride)[:, 0], dev) if args.stage in ("both", "b") else None
         if ev:
             ev[0].record()
         out_a = None

@@ -84,7 +84,7 @@ _SIGNATURES = {
     "cnrma_to_channels_last": (C.c_int, [C.POINTER(Features), C.c_void_p, C.c_void_p]),
     "cnrma_t_one": (C.c_float, [C.POINTER(Grid), C.c_double, C.c_int]),
     "cnrma_ray_parameters": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "cnrma_rma_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+    "cnrma_rma_workspace_bytes": (C.c_int, [C.POINTER(Grid), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                                             C.POINTER(C.c_size_t)]),
     "cnrma_rma_march": (C.c_int, [C.POINTER(Grid), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                   C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,

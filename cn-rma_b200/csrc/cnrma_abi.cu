@@ -156,12 +156,12 @@ int cnrma_ray_parameters(const float *pinv, int views, int height, int width, fl
     return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
 }
 
-int cnrma_rma_workspace_bytes(int views, int height, int width, int grids, int mode, float threshold,
-                              int depth_points, size_t *bytes) {
-    if (!bytes || views <= 0 || height <= 0 || width <= 0 || grids <= 0) return CNRMA_ERR_ARG;
+int cnrma_rma_workspace_bytes(const cnrma_grid *grid, int views, int height, int width, int grids, int mode,
+                              float threshold, int depth_points, size_t *bytes) {
+    if (!grid_ok(grid) || !bytes || views <= 0 || height <= 0 || width <= 0 || grids <= 0) return CNRMA_ERR_ARG;
     if (mode != CNRMA_MARCH_NEUS && mode != CNRMA_MARCH_DEPTH) return CNRMA_ERR_ARG;
     if (mode == CNRMA_MARCH_DEPTH && depth_points < 0) return CNRMA_ERR_ARG;
-    *bytes = rma_workspace(views, height, width, grids, mode, threshold, depth_points).total;
+    *bytes = rma_workspace(views, height, width, grids, mode, threshold, depth_points, rma_brick_count(to_dev(*grid))).total;
     return CNRMA_OK;
 }
 
@@ -170,13 +170,14 @@ int cnrma_rma_march(const cnrma_grid *grid, const float *pinv, int views, int he
                     size_t workspace_bytes, cnrma_rma_result *result, void *stream) {
     if (!grid_ok(grid) || !pinv || !tsdf || !workspace || !result) return CNRMA_ERR_ARG;
     size_t need = 0;
-    const int s = cnrma_rma_workspace_bytes(views, height, width, grids, mode, threshold, depth_points, &need);
+    const int s = cnrma_rma_workspace_bytes(grid, views, height, width, grids, mode, threshold, depth_points, &need);
     if (s != CNRMA_OK) return s;
     if (workspace_bytes < need) return CNRMA_ERR_CAPACITY;
     if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) return CNRMA_ERR_LAYOUT;
     const int d = device_ok();
     if (d != CNRMA_OK) return d;
-    const RmaWorkspace ws = rma_workspace(views, height, width, grids, mode, threshold, depth_points);
+    const RmaWorkspace ws = rma_workspace(views, height, width, grids, mode, threshold, depth_points,
+                                          rma_brick_count(to_dev(*grid)));
     if (ws.blocks >= ((int64_t)1 << 31)) return CNRMA_ERR_UNSUPPORTED;
     const cudaError_t e = run_march(to_dev(*grid), pinv, views, height, width, tsdf, grids, t_one, mode, threshold,
                                     depth_points, workspace, ws, result, static_cast<cudaStream_t>(stream));

@@ -27,7 +27,8 @@ int rma_record_capacity(int grids, int mode, float threshold, int depth_points) 
     return grids;
 }
 
-RmaWorkspace rma_workspace(int views, int height, int width, int grids, int mode, float threshold, int depth_points) {
+RmaWorkspace rma_workspace(int views, int height, int width, int grids, int mode, float threshold, int depth_points,
+                           int64_t bricks) {
     RmaWorkspace w;
     w.rays = (int64_t)views * height * width;
     w.blocks = (w.rays + kRayThreads - 1) / kRayThreads;
@@ -39,6 +40,7 @@ RmaWorkspace rma_workspace(int views, int height, int width, int grids, int mode
     w.off_blk_off = o;  o = align256(o + sizeof(int64_t) * (size_t)w.blocks);
     w.off_rec_w = o;    o = align256(o + sizeof(float) * (size_t)w.rays * (size_t)w.cap);
     w.off_rec_i = o;    o = align256(o + sizeof(float) * (size_t)w.rays * (size_t)w.cap);
+    w.off_bricks = o;   o = align256(o + (size_t)bricks);
     w.total = o;
     return w;
 }
@@ -57,6 +59,8 @@ struct MarchParams {
     double *blk_wsum;
     float *rec_w, *rec_i;
     cnrma_rma_result *result;
+    const uint8_t *bricks;   // [nbx,nby,nbz] 1 = every voxel of the brick holds the same TSDF value
+    int nby, nbz;
 };
 
 // Per-ray constants of the position -> voxel id mapping.
@@ -65,31 +69,115 @@ struct VoxelMap {
     bool zero_origin;  // origin == (0,0,0): `places - origin` is the identity and is skipped
 };
 
-// round((p - origin) / voxel_size) for one coordinate (rm.py:730: sub, true division, half-to-even).
+// round((p - origin) / voxel_size) per coordinate (rm.py:730: sub, true division, half-to-even).
 // The quotient is only needed rounded to an integer, so the IEEE division is replaced by a multiplication with
 // the rounded reciprocal whenever that provably cannot change the result: q_fast = RN(rel * RN(1/vs)) is
 // within |q| * 2^-23 of the exact quotient, hence rint(q_fast) == rint(RN(rel / vs)) unless q_fast lies within
 // |q| * 2^-22 of a half-integer -- in which case (about one sample in 10^4) the division is done for real.
-__device__ __forceinline__ float voxel_coord(float p, float o, float vs, const VoxelMap &m) {
-    const float rel = m.zero_origin ? p : __fsub_rn(p, o);
-    const float q = __fmul_rn(rel, m.inv_vs);
-    float r = rintf(q);
-    const float frac = __fsub_rn(q, r);
-    const float safe = __fmaf_rn(fabsf(q), -2.384185791015625e-07f, 0.5f);   // 0.5 - |q| * 2^-22
-    if (!(fabsf(frac) < safe)) r = rintf(__fdiv_rn(rel, vs));   // also taken for NaN / huge q
-    return r;
+//
+// One sample of a ray (rm.py:729-733): position -> rounded voxel id; returns the flat id or -1 outside the grid
+// (ix, iy, iz are the integer coordinates when inside).  Callers guarantee finite o, d (non-finite rays keep
+// nothing in the reference either: their ids convert to INT64_MIN and fail the bounds test).
+__device__ __forceinline__ int sample_voxel(const GridDev &g, const VoxelMap &m, const float o[3], const float d[3],
+                                            float t, int &ix, int &iy, int &iz) {
+    const float org[3] = {g.ox, g.oy, g.oz};
+    float rel[3], r[3];
+    bool ambiguous = false;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float p = __fadd_rn(o[a], __fmul_rn(d[a], t));
+        rel[a] = m.zero_origin ? p : __fsub_rn(p, org[a]);
+        const float q = __fmul_rn(rel[a], m.inv_vs);
+        r[a] = rintf(q);
+        const float safe = __fmaf_rn(fabsf(q), -2.384185791015625e-07f, 0.5f);   // 0.5 - |q| * 2^-22
+        ambiguous = ambiguous || !(fabsf(__fsub_rn(q, r[a])) < safe);             // also true for huge q
+    }
+    if (ambiguous) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) r[a] = rintf(__fdiv_rn(rel[a], g.vs));
+    }
+    // integer-valued floats; __float2int_rn saturates, so far-away samples simply fail the unsigned range test
+    ix = __float2int_rn(r[0]);
+    iy = __float2int_rn(r[1]);
+    iz = __float2int_rn(r[2]);
+    const bool inb = ((unsigned)ix < (unsigned)g.nx) && ((unsigned)iy < (unsigned)g.ny) && ((unsigned)iz < (unsigned)g.nz);
+    return inb ? ((ix * g.ny + iy) * g.nz + iz) : -1;
 }
 
-// One sample of a ray (rm.py:729-733): position -> rounded voxel id; returns the flat id or -1 outside the grid.
 __device__ __forceinline__ int sample_voxel(const GridDev &g, const VoxelMap &m, const float o[3], const float d[3],
                                             float t) {
-    const float qx = voxel_coord(__fadd_rn(o[0], __fmul_rn(d[0], t)), g.ox, g.vs, m);
-    const float qy = voxel_coord(__fadd_rn(o[1], __fmul_rn(d[1], t)), g.oy, g.vs, m);
-    const float qz = voxel_coord(__fadd_rn(o[2], __fmul_rn(d[2], t)), g.oz, g.vs, m);
-    // integer-valued floats (or NaN / inf, which fail every comparison like the reference's INT64_MIN)
-    const bool inb = (qx >= 0.0f) && (qx < (float)g.nx) && (qy >= 0.0f) && (qy < (float)g.ny) && (qz >= 0.0f) &&
-                     (qz < (float)g.nz);
-    return inb ? (((int)qx * g.ny + (int)qy) * g.nz + (int)qz) : -1;
+    int ix, iy, iz;
+    return sample_voxel(g, m, o, d, t, ix, iy, iz);
+}
+
+__device__ __forceinline__ bool ray_is_finite(const float o[3], const float d[3]) {
+    return isfinite(o[0] + o[1] + o[2]) && isfinite(d[0] + d[1] + d[2]);
+}
+
+// ---- uniform-brick skipping ------------------------------------------------------------------------------
+// The TSDF the reference marches through is piecewise constant over large regions (free space and unobserved
+// space are set to +-0.999 by the coarse-to-fine head, atlas_head.py:47).  Consecutive samples that read the
+// same value have alpha == 0 exactly, so a run of samples inside a brick whose voxels all hold one value
+// changes neither the transmittance nor (for thr > 0) the kept set, and can be jumped over.  The jump is
+// conservative: only steps whose position lies inside the brick shrunk by kBrickMargin voxels on every side
+// (far more than the fp32 error of o + d*t) are skipped, and the step after the jump is marched normally.
+constexpr int kBrickShift = 2;                 // 4^3-voxel bricks
+constexpr int kBrick = 1 << kBrickShift;
+constexpr float kBrickMargin = 0.05f;          // voxels
+
+// one warp per brick: 64 voxels, two per lane
+__global__ void __launch_bounds__(256) tsdf_bricks_kernel(GridDev g, const float *__restrict__ tsdf, int nbx, int nby,
+                                                          int nbz, uint8_t *__restrict__ bricks) {
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= nbx * nby * nbz) return;
+    const int bz = b % nbz, bxy = b / nbz, by = bxy % nby, bx = bxy / nby;
+    const int x0 = bx << kBrickShift, y0 = by << kBrickShift, z0 = bz << kBrickShift;
+    const uint32_t ref = __float_as_uint(__ldg(tsdf + (x0 * g.ny + y0) * g.nz + z0));
+    bool same = true;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int v = lane + 32 * k;   // (x, y, z) = (v / 16, (v / 4) % 4, v % 4), clamped at the grid border
+        const int x = min(x0 + (v >> 4), g.nx - 1), y = min(y0 + ((v >> 2) & 3), g.ny - 1), z = min(z0 + (v & 3), g.nz - 1);
+        same = same && (__float_as_uint(__ldg(tsdf + (x * g.ny + y) * g.nz + z)) == ref);
+    }
+    same = __all_sync(0xffffffffu, same);
+    if (lane == 0) bricks[b] = (uint8_t)same;
+}
+
+// Per-ray constants of the brick exit test: the ray leaves the brick of voxel c through the face
+// c_lo + face_a (in rounded voxel coordinates) at t_a = t0_a + (c_lo + face_a) * dt_a.
+struct BrickRay {
+    float t0[3], dt[3], face[3];
+    float inv_t_one;
+};
+
+__device__ __forceinline__ BrickRay make_brick_ray(const GridDev &g, const float o[3], const float d[3], float t_one) {
+    BrickRay b;
+    const float org[3] = {g.ox, g.oy, g.oz};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float inv_d = 1.0f / d[a];                     // +-inf for axis-parallel rays: that face is never reached
+        b.t0[a] = (org[a] - o[a]) * inv_d;
+        b.dt[a] = g.vs * inv_d;
+        // the brick spans voxel centres lo .. lo+kBrick-1, i.e. rounded coordinates in [lo-0.5, lo+kBrick-0.5]
+        b.face[a] = (inv_d >= 0.0f) ? ((float)kBrick - 0.5f - kBrickMargin) : (-0.5f + kBrickMargin);
+    }
+    b.inv_t_one = 1.0f / t_one;
+    return b;
+}
+
+// Last step index that is certainly still inside the brick containing voxel (ix,iy,iz); -1 if none.
+__device__ __forceinline__ int brick_exit_step(const BrickRay &b, int ix, int iy, int iz) {
+    const int c[3] = {ix, iy, iz};
+    float t_exit = 3.0e38f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float edge = (float)(c[a] & ~(kBrick - 1)) + b.face[a];
+        t_exit = fminf(t_exit, b.t0[a] + edge * b.dt[a]);   // NaN (0 * inf, inf - inf) is ignored by fminf
+    }
+    const float steps = t_exit * b.inv_t_one - 1.0f;        // one more step of slack
+    return (steps > 0.0f && steps < 1.0e9f) ? (int)steps : -1;
 }
 
 __device__ __forceinline__ VoxelMap make_voxel_map(const GridDev &g) {
@@ -151,18 +239,34 @@ __global__ void __launch_bounds__(kRayThreads) march_neus_kernel(const __grid_co
         const VoxelMap vm = make_voxel_map(p.g);
         const bool keep_zero = !(p.thr > 0.0f);   // thr <= 0 (or NaN): zero weights pass `w >= thr` too
 
+        const BrickRay br = make_brick_ray(p.g, o, d, p.t_one);
+        const bool can_skip = !keep_zero && p.bricks != nullptr;
+        int last_brick = -1;
+        const int n_steps = ray_is_finite(o, d) ? p.N : -1;   // non-finite rays keep nothing (see sample_voxel)
+
         float T = 1.0f;
         float tv_cur = 1.0f, s_cur = 0.0f;   // TSDF value / sigmoid of the current sample (set at i == 0)
         int vox_cur = -1;
         bool entered = false;
         int overflow = 0;
-        for (int i = 0; i <= p.N; ++i) {
+        for (int i = 0; i <= n_steps; ++i) {
             int vox_next = -1;
+            int skip_to = -1;
             float tv_next = tv_cur;   // i == N: last sample repeated (rm.py:758)
             if (i < p.N) {
-                vox_next = sample_voxel(p.g, vm, o, d, __fmul_rn((float)i, p.t_one));
+                int ix, iy, iz;
+                vox_next = sample_voxel(p.g, vm, o, d, __fmul_rn((float)i, p.t_one), ix, iy, iz);
                 // samples outside the grid read tsdf = 1.0 (rm.py:744); same voxel -> same value
-                if (i == 0 || vox_next != vox_cur) tv_next = (vox_next >= 0) ? __ldg(p.tsdf + vox_next) : 1.0f;
+                if (i == 0 || vox_next != vox_cur) {
+                    tv_next = (vox_next >= 0) ? __ldg(p.tsdf + vox_next) : 1.0f;
+                    if (can_skip && vox_next >= 0) {
+                        const int brick = ((ix >> kBrickShift) * p.nby + (iy >> kBrickShift)) * p.nbz + (iz >> kBrickShift);
+                        if (brick != last_brick) {
+                            last_brick = brick;
+                            if (__ldg(p.bricks + brick)) skip_to = brick_exit_step(br, ix, iy, iz);
+                        }
+                    }
+                }
             }
             float s_next = s_cur;
             if (i == 0 || tv_next != tv_cur) s_next = sigmoid_neg(tv_next);
@@ -191,6 +295,9 @@ __global__ void __launch_bounds__(kRayThreads) march_neus_kernel(const __grid_co
             tv_cur = tv_next;
             s_cur = s_next;
             vox_cur = vox_next;
+            // samples i+1 .. skip_to all lie in this uniform brick: they read tv_cur, so alpha == 0 and nothing
+            // changes; resume with sample skip_to + 1 (never past the repeated last sample)
+            if (skip_to > i) i = min(skip_to, p.N - 1);
         }
         p.counts[ray] = kept;
         if (overflow) atomicAdd(&p.result->overflow, 1);
@@ -214,7 +321,8 @@ __global__ void __launch_bounds__(kRayThreads) march_depth_kernel(const __grid_c
         int best = -1;
         float tv_cur = 1.0f;
         int vox_cur = -1;
-        for (int i = 0; i < p.N; ++i) {
+        const int n_steps = ray_is_finite(o, d) ? p.N : 0;   // non-finite rays: every sample reads 1.0, no crossing
+        for (int i = 0; i < n_steps; ++i) {
             const int vox = sample_voxel(p.g, vm, o, d, __fmul_rn((float)i, p.t_one));
             const float tv = (i > 0 && vox == vox_cur) ? tv_cur : ((vox >= 0) ? __ldg(p.tsdf + vox) : 1.0f);
             if (i > 0 && __fmul_rn(tv_cur, tv) <= 0.0f) {
@@ -375,30 +483,27 @@ __global__ void __launch_bounds__(kRayThreads) fill_rows_kernel(const __grid_con
         float o[3], d[3];
         ray_of_pixel(p.pinv + 16 * view, u, v, o, d);
         const T *feat = static_cast<const T *>(p.views[view - p.view_base]) + (int64_t)v * p.stride_y + (int64_t)u * p.stride_x;
-        // records of this ray: lane k holds record k (cap <= 32 is the common case; loop otherwise)
-        for (int cbase = 0; cbase < p.C; cbase += 32 * kFillRegs) {
-            float f[kFillRegs];
-#pragma unroll
-            for (int j = 0; j < kFillRegs; ++j) {
-                const int c = cbase + j * 32 + lane;
-                f[j] = (c < p.C) ? load_feat<T>(feat + c) : 0.0f;
-            }
-            for (int k = 0; k < cnt; ++k) {
-                const float w = __ldg(p.rec_w + (int64_t)k * p.rays + ray);
-                const float fi = __ldg(p.rec_i + (int64_t)k * p.rays + ray);
+        // records in chunks of 32: lane k prepares record k0 + k (position, scaled weight, target voxel) and writes
+        // the row's leading columns; the feature columns are then streamed row by row with the weight broadcast
+        for (int k0 = 0; k0 < cnt; k0 += 32) {
+            const int nk = min(32, cnt - k0);
+            float wk = 0.0f;       // weight that multiplies the features of this lane's record
+            int64_t vox = -1;      // scatter target
+            if (lane < nk) {
+                const float w = __ldg(p.rec_w + (int64_t)(k0 + lane) * p.rays + ray);
+                const float fi = __ldg(p.rec_i + (int64_t)(k0 + lane) * p.rays + ray);
                 float pos[3];
                 record_position(p, o, d, fi, pos);
                 if (!SCATTER) {
-                    float *row = p.rows + (off + k) * p.row_stride;
-                    const float wn = p.normalize ? __fdiv_rn(w, mean) : 1.0f;   // weights / mean(weights), rm.py:303
-                    if (cbase == 0) {
-                        if (lane < 3) row[lane] = pos[lane];
-                        if (lane == 3 && !p.normalize) row[3] = w;
-                    }
-#pragma unroll
-                    for (int j = 0; j < kFillRegs; ++j) {
-                        const int c = cbase + j * 32 + lane;
-                        if (c < p.C) __stcs(row + col0 + c, p.normalize ? __fmul_rn(f[j], wn) : f[j]);
+                    float *row = p.rows + (off + k0 + lane) * p.row_stride;
+                    row[0] = pos[0];
+                    row[1] = pos[1];
+                    row[2] = pos[2];
+                    if (p.normalize) {
+                        wk = __fdiv_rn(w, mean);   // weights / mean(weights), rm.py:303
+                    } else {
+                        row[3] = w;
+                        wk = 1.0f;
                     }
                 } else {
                     const float qx = rintf(__fdiv_rn(__fsub_rn(pos[0], p.g.ox), p.g.vs));
@@ -406,18 +511,152 @@ __global__ void __launch_bounds__(kRayThreads) fill_rows_kernel(const __grid_con
                     const float qz = rintf(__fdiv_rn(__fsub_rn(pos[2], p.g.oz), p.g.vs));
                     const bool inb = (qx >= 0.0f) && (qx < (float)p.g.nx) && (qy >= 0.0f) && (qy < (float)p.g.ny) &&
                                      (qz >= 0.0f) && (qz < (float)p.g.nz);
-                    if (!inb) continue;
-                    const int64_t vox = ((int64_t)(int)qx * p.g.ny + (int)qy) * p.g.nz + (int)qz;
-                    if (cbase == 0 && lane == 0) atomicAdd(p.wtot + vox, w);
+                    if (inb) {
+                        vox = ((int64_t)(int)qx * p.g.ny + (int)qy) * p.g.nz + (int)qz;
+                        atomicAdd(p.wtot + vox, w);
+                    }
+                    wk = w;
+                }
+            }
+            for (int cbase = 0; cbase < p.C; cbase += 32 * kFillRegs) {
+                float f[kFillRegs];
 #pragma unroll
-                    for (int j = 0; j < kFillRegs; ++j) {
-                        const int c = cbase + j * 32 + lane;
-                        if (c < p.C) atomicAdd(p.wsum + vox * p.C + c, __fmul_rn(w, f[j]));
+                for (int j = 0; j < kFillRegs; ++j) {
+                    const int c = cbase + j * 32 + lane;
+                    f[j] = (c < p.C) ? load_feat<T>(feat + c) : 0.0f;
+                }
+                for (int k = 0; k < nk; ++k) {
+                    const float wn = __shfl_sync(0xffffffffu, wk, k);
+                    if (!SCATTER) {
+                        float *dst = p.rows + (off + k0 + k) * p.row_stride + col0;
+#pragma unroll
+                        for (int j = 0; j < kFillRegs; ++j) {
+                            const int c = cbase + j * 32 + lane;
+                            if (c < p.C) __stcs(dst + c, p.normalize ? __fmul_rn(f[j], wn) : f[j]);
+                        }
+                    } else {
+                        const int64_t tv = __shfl_sync(0xffffffffu, vox, k);
+                        if (tv < 0) continue;
+#pragma unroll
+                        for (int j = 0; j < kFillRegs; ++j) {
+                            const int c = cbase + j * 32 + lane;
+                            if (c < p.C) atomicAdd(p.wsum + tv * p.C + c, __fmul_rn(wn, f[j]));
+                        }
                     }
                 }
             }
         }
     }
+}
+
+// ---- fill, TMA-store variant ---------------------------------------------------------------------------
+// Rows are 4*(3+C) bytes -- 1036 for C = 256 -- so consecutive rows are only 4-byte aligned and plain stores
+// reach ~4.8 TB/s (profiles/microbench/store_paths.cu).  The rows of one ray are contiguous in the output, so
+// each warp assembles a batch of them in a shared-memory staging buffer that mirrors the global byte range
+// (same offset modulo 16), pushes the 16-byte aligned interior with ONE bulk asynchronous store (TMA,
+// cp.async.bulk.global.shared) and writes the few unaligned floats at either end itself: ~6.3 TB/s.
+constexpr int kStageBytes = 8192;   // per-warp staging buffer; 3 CTAs x 8 warps x 8 KB = 192 KB per SM
+
+template <typename T>
+__global__ void __launch_bounds__(kRayThreads) fill_rows_tma_kernel(const __grid_constant__ FillParams p) {
+    extern __shared__ __align__(128) unsigned char stage_raw[];
+    __shared__ int s_warp_rows[kRayThreads / kWarp];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *stage = reinterpret_cast<float *>(stage_raw + (size_t)warp * kStageBytes);
+    const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(stage);
+    const int hw = p.H * p.W;
+    const int64_t ray0 = (int64_t)p.view_base * hw + (int64_t)blockIdx.x * kRayThreads;
+    const int64_t my_ray = ray0 + threadIdx.x;
+    const int64_t ray_end = (int64_t)(p.view_base + p.V) * hw;
+    const int my_cnt = (my_ray < ray_end && my_ray < p.rays) ? p.counts[my_ray] : 0;
+    int incl = my_cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) s_warp_rows[warp] = incl;
+    __syncthreads();
+    int64_t base = p.blk_off[ray0 / kRayThreads];
+    for (int i = 0; i < warp; ++i) base += s_warp_rows[i];
+    const int64_t my_off = base + (incl - my_cnt);
+    const float mean = p.normalize ? __ldg(p.mean) : 1.0f;
+    const int col0 = p.normalize ? 3 : 4;
+    const int cols = p.C + col0;
+    const int row_bytes = cols * 4;
+    const int rows_per_batch = (kStageBytes - 16) / row_bytes;
+
+    for (int r = 0; r < 32; ++r) {
+        const int cnt = __shfl_sync(0xffffffffu, my_cnt, r);
+        if (cnt == 0) continue;
+        const int64_t off = __shfl_sync(0xffffffffu, my_off, r);
+        const int64_t ray = ray0 + warp * 32 + r;
+        const int view = (int)(ray / hw);
+        const int pix = (int)(ray % hw);
+        const int u = pix % p.W, v = pix / p.W;
+        float o[3], d[3];
+        ray_of_pixel(p.pinv + 16 * view, u, v, o, d);
+        const T *feat = static_cast<const T *>(p.views[view - p.view_base]) + (int64_t)v * p.stride_y + (int64_t)u * p.stride_x;
+        float f[kFillRegs];
+#pragma unroll
+        for (int j = 0; j < kFillRegs; ++j) {
+            const int c = j * 32 + lane;
+            f[j] = (c < p.C) ? load_feat<T>(feat + c) : 0.0f;
+        }
+        for (int k0 = 0; k0 < cnt; k0 += 32) {
+            const int nk = min(32, cnt - k0);
+            float wk = 0.0f, wraw = 0.0f, pos[3] = {0.0f, 0.0f, 0.0f};
+            if (lane < nk) {
+                wraw = __ldg(p.rec_w + (int64_t)(k0 + lane) * p.rays + ray);
+                const float fi = __ldg(p.rec_i + (int64_t)(k0 + lane) * p.rays + ray);
+                record_position(p, o, d, fi, pos);
+                wk = p.normalize ? __fdiv_rn(wraw, mean) : 1.0f;   // weights / mean(weights), rm.py:303
+            }
+            for (int kb = 0; kb < nk; kb += rows_per_batch) {
+                const int nb = min(rows_per_batch, nk - kb);
+                unsigned char *gbase = reinterpret_cast<unsigned char *>(p.rows) + (off + k0 + kb) * (int64_t)row_bytes;
+                const int h = (int)(reinterpret_cast<uintptr_t>(gbase) & 15);   // same offset modulo 16 in the buffer
+                const int hw4 = h >> 2;
+                // the previous bulk store must have finished reading the buffer
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+                for (int k = 0; k < nb; ++k) {
+                    const float wn = __shfl_sync(0xffffffffu, wk, kb + k);
+                    float *row = stage + hw4 + k * cols + col0;
+#pragma unroll
+                    for (int j = 0; j < kFillRegs; ++j) {
+                        const int c = j * 32 + lane;
+                        if (c < p.C) row[c] = p.normalize ? __fmul_rn(f[j], wn) : f[j];
+                    }
+                }
+                if (lane >= kb && lane < kb + nb) {
+                    float *row = stage + hw4 + (lane - kb) * cols;
+                    row[0] = pos[0];
+                    row[1] = pos[1];
+                    row[2] = pos[2];
+                    if (!p.normalize) row[3] = wraw;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                const int total = nb * row_bytes;
+                const int a0 = (h + 15) & ~15;            // first 16-byte aligned buffer offset inside the data
+                const int a1 = (h + total) & ~15;         // end of the aligned interior
+                if (lane == 0 && a1 > a0) {
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gbase - h + a0),
+                                 "r"(stage_addr + (uint32_t)a0), "r"((uint32_t)(a1 - a0))
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                // unaligned floats in front of / behind the interior (at most 3 each)
+                const int head = (min(a0, h + total) - h) >> 2;
+                const int tail_lo = max(a1, a0);
+                const int tail = (h + total > tail_lo) ? ((h + total - tail_lo) >> 2) : 0;
+                if (lane < head) reinterpret_cast<float *>(gbase)[lane] = stage[hw4 + lane];
+                if (lane < tail) reinterpret_cast<float *>(gbase - h + tail_lo)[lane] = stage[(tail_lo >> 2) + lane];
+            }
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // Dense view of the records for parity tests: weights * valid_final and valid_final (rm.py:765-767).
@@ -479,8 +718,21 @@ cudaError_t run_march(const GridDev &g, const float *pinv, int V, int H, int W, 
     p.rec_w = reinterpret_cast<float *>(base + ws.off_rec_w);
     p.rec_i = reinterpret_cast<float *>(base + ws.off_rec_i);
     p.result = result;
+    p.bricks = nullptr;
+    p.nby = p.nbz = 0;
     cudaError_t err = cudaMemsetAsync(result, 0, sizeof(cnrma_rma_result), stream);
     if (err != cudaSuccess) return err;
+    if (mode == CNRMA_MARCH_NEUS && thr > 0.0f) {
+        const int nbx = (g.nx + kBrick - 1) >> kBrickShift;
+        p.nby = (g.ny + kBrick - 1) >> kBrickShift;
+        p.nbz = (g.nz + kBrick - 1) >> kBrickShift;
+        uint8_t *bricks = reinterpret_cast<uint8_t *>(base + ws.off_bricks);
+        const int nb = nbx * p.nby * p.nbz;
+        tsdf_bricks_kernel<<<(nb + 7) / 8, 256, 0, stream>>>(g, tsdf, nbx, p.nby, p.nbz, bricks);
+        err = cudaGetLastError();
+        if (err != cudaSuccess) return err;
+        p.bricks = bricks;
+    }
     if (mode == CNRMA_MARCH_DEPTH)
         march_depth_kernel<<<(unsigned)ws.blocks, kRayThreads, 0, stream>>>(p);
     else
@@ -513,10 +765,24 @@ static cudaError_t launch_fill(FillParams &p, int dtype, const void *const *view
         for (int i = 0; i < nv; ++i) p.views[i] = view_ptrs_host[v0 + i];
         const int64_t rays = (int64_t)nv * hw;
         const unsigned blocks = (unsigned)((rays + kRayThreads - 1) / kRayThreads);
-        if (dtype == CNRMA_BF16)
+        // packed rows (row_stride == columns) of up to 256 channels take the TMA-store kernel
+        const int cols = p.C + (p.normalize ? 3 : 4);
+        const bool tma = !SCATTER && p.row_stride == cols && p.C <= 32 * kFillRegs && cols * 4 <= kStageBytes - 16 &&
+                         reinterpret_cast<uintptr_t>(p.rows) % 4 == 0;
+        if (tma) {
+            const size_t smem = (size_t)(kRayThreads / kWarp) * kStageBytes;
+            if (dtype == CNRMA_BF16) {
+                cudaFuncSetAttribute(fill_rows_tma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                fill_rows_tma_kernel<__nv_bfloat16><<<blocks, kRayThreads, smem, stream>>>(p);
+            } else {
+                cudaFuncSetAttribute(fill_rows_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                fill_rows_tma_kernel<float><<<blocks, kRayThreads, smem, stream>>>(p);
+            }
+        } else if (dtype == CNRMA_BF16) {
             fill_rows_kernel<__nv_bfloat16, SCATTER><<<blocks, kRayThreads, 0, stream>>>(p);
-        else
+        } else {
             fill_rows_kernel<float, SCATTER><<<blocks, kRayThreads, 0, stream>>>(p);
+        }
         const cudaError_t err = cudaGetLastError();
         if (err != cudaSuccess) return err;
     }
@@ -564,4 +830,11 @@ cudaError_t run_expand(int64_t rays, int N, const void *workspace, const RmaWork
     return cudaGetLastError();
 }
 
+}  // namespace cnrma
+
+namespace cnrma {
+int64_t rma_brick_count(const GridDev &g) {
+    return (int64_t)((g.nx + kBrick - 1) >> kBrickShift) * ((g.ny + kBrick - 1) >> kBrickShift) *
+           ((g.nz + kBrick - 1) >> kBrickShift);
+}
 }  // namespace cnrma

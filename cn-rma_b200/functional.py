@@ -287,7 +287,7 @@ def _march(fs, b, P_scaled_b, tsdf_b, grid, voxel_dim, voxel_size, grids, mode, 
     m.pinv = pinv if pinv is not None else prepare_pinv(P_scaled_b, device)
     m.t_one = lib.cnrma_t_one(C.byref(grid), float(voxel_size), m.grids)
     nbytes = C.c_size_t(0)
-    _lib.check(lib.cnrma_rma_workspace_bytes(fs.V, fs.H, fs.W, m.grids, m.mode, m.threshold, m.depth_points,
+    _lib.check(lib.cnrma_rma_workspace_bytes(C.byref(grid), fs.V, fs.H, fs.W, m.grids, m.mode, m.threshold, m.depth_points,
                                              C.byref(nbytes)), "cnrma_rma_workspace_bytes")
     m.workspace = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
     m.result = torch.empty(C.sizeof(_lib.RmaResult), dtype=torch.uint8, device=device)

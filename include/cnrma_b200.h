@@ -135,8 +135,8 @@ float cnrma_t_one(const cnrma_grid *grid, double voxel_size, int grids);
 int cnrma_ray_parameters(const float *pinv, int views, int height, int width, float *o, float *d, void *stream);
 
 /* Bytes of scratch cnrma_rma_march / _fill / _scatter need for `views` x H x W rays. */
-int cnrma_rma_workspace_bytes(int views, int height, int width, int grids, int mode, float threshold,
-                              int depth_points, size_t *bytes);
+int cnrma_rma_workspace_bytes(const cnrma_grid *grid, int views, int height, int width, int grids, int mode,
+                              float threshold, int depth_points, size_t *bytes);
 
 /* Replaces get_ray_parameter (rm.py:71-111; the 4x4 inverses are an input, see below) and the march /
  * weight / selection part of ray_projection_neus (rm.py:710-767) or ray_projection_depth

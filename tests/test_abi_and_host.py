@@ -64,11 +64,12 @@ def test_t_one_matches_reference_formula():
 def test_workspace_query():
     lib = cn.load()
     n = C.c_size_t(0)
-    assert lib.cnrma_rma_workspace_bytes(50, 120, 160, 300, 0, 0.05, 0, C.byref(n)) == 0
+    g = _lib.make_grid((80, 80, 32), 0.08, (0, 0, 0))
+    assert lib.cnrma_rma_workspace_bytes(C.byref(g), 50, 120, 160, 300, 0, 0.05, 0, C.byref(n)) == 0
     rays = 50 * 120 * 160
     assert n.value >= rays * 4 + 2 * rays * 21 * 4          # counts + (step, weight) records, 1/0.05 + 1 per ray
-    assert lib.cnrma_rma_workspace_bytes(0, 120, 160, 300, 0, 0.05, 0, C.byref(n)) == -1
-    assert lib.cnrma_rma_workspace_bytes(1, 1, 1, 1, 7, 0.05, 0, C.byref(n)) == -1
+    assert lib.cnrma_rma_workspace_bytes(C.byref(g), 0, 120, 160, 300, 0, 0.05, 0, C.byref(n)) == -1
+    assert lib.cnrma_rma_workspace_bytes(C.byref(g), 1, 1, 1, 1, 7, 0.05, 0, C.byref(n)) == -1
 
 
 def test_scale_and_invert_projections_follow_reference_ops():
