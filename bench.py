@@ -213,6 +213,7 @@ def main():
     # --- one step, with CUDA events between the phases (all on the current stream) ---------------------
     fs = F._FeatureStack(F._as_view_list(feats), need_vector_layout=True)
     grid = _lib.make_grid(sc.voxel_dim, sc.voxel_size, sc.origin)
+    fill_desc = fs.descriptor(0)
 
     def step(ev=None):
         # host half of the ray set-up first (4x4 LAPACK inverses, rm.py:96-102), so that it overlaps with the
@@ -233,7 +234,7 @@ def main():
                 ev[2].record()
             res = F._read_result(m)              # the path's one host sync: M sizes the output
             m_rows = int(res.rows)
-            rows = F._fill(fs, 0, m, grid, m_rows, True)
+            rows = F._fill(fs, 0, m, grid, m_rows, True, None, fill_desc)
         elif ev:
             ev[2].record()
         if ev:

@@ -161,7 +161,8 @@ int cnrma_rma_workspace_bytes(const cnrma_grid *grid, int views, int height, int
     if (!grid_ok(grid) || !bytes || views <= 0 || height <= 0 || width <= 0 || grids <= 0) return CNRMA_ERR_ARG;
     if (mode != CNRMA_MARCH_NEUS && mode != CNRMA_MARCH_DEPTH) return CNRMA_ERR_ARG;
     if (mode == CNRMA_MARCH_DEPTH && depth_points < 0) return CNRMA_ERR_ARG;
-    *bytes = rma_workspace(views, height, width, grids, mode, threshold, depth_points, rma_brick_count(to_dev(*grid))).total;
+    *bytes = rma_workspace(views, height, width, grids, mode, threshold, depth_points, rma_brick_count(to_dev(*grid)),
+                           (int64_t)grid->nx * grid->ny * grid->nz).total;
     return CNRMA_OK;
 }
 
@@ -177,7 +178,7 @@ int cnrma_rma_march(const cnrma_grid *grid, const float *pinv, int views, int he
     const int d = device_ok();
     if (d != CNRMA_OK) return d;
     const RmaWorkspace ws = rma_workspace(views, height, width, grids, mode, threshold, depth_points,
-                                          rma_brick_count(to_dev(*grid)));
+                                          rma_brick_count(to_dev(*grid)), (int64_t)grid->nx * grid->ny * grid->nz);
     if (ws.blocks >= ((int64_t)1 << 31)) return CNRMA_ERR_UNSUPPORTED;
     const cudaError_t e = run_march(to_dev(*grid), pinv, views, height, width, tsdf, grids, t_one, mode, threshold,
                                     depth_points, workspace, ws, result, static_cast<cudaStream_t>(stream));

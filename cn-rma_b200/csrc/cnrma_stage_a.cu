@@ -267,16 +267,27 @@ static cudaError_t launch_agg(const AggParams &p, int chunks, cudaStream_t strea
     const size_t head = (8 * (kAggThreads / kWarp) + sizeof(void *) * p.V + sizeof(float) * 12 * Vpad + 127) & ~(size_t)127;
     const size_t smem = head + (size_t)(kAggThreads / kWarp) * p.rows_cap * p.chunk_bytes;
     auto kernel = aggregate_views_kernel<VPL, T>;
-    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // launch configuration cached per (kernel instantiation, device, smem size): the attribute / occupancy queries
+    // cost more than the launch itself
+    struct Cached { int dev = -1; size_t smem = 0; int ctas = 0; };
+    static thread_local Cached cache;
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
     if (err != cudaSuccess) return err;
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kAggThreads, smem);
-    if (err != cudaSuccess) return err;
-    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    if (cache.dev != dev || cache.smem != smem) {
+        err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        int sms = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kAggThreads, smem);
+        if (err != cudaSuccess) return err;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        cache.dev = dev;
+        cache.smem = smem;
+        cache.ctas = sms * per_sm;
+    }
+    const int persistent = cache.ctas;
     const int needed = (p.nvox + (kAggThreads / kWarp) - 1) / (kAggThreads / kWarp);
-    const int persistent = sms * per_sm;
     const dim3 grid(needed < persistent ? needed : persistent, chunks);
     kernel<<<grid, kAggThreads, smem, stream>>>(p);
     return cudaGetLastError();

@@ -28,7 +28,7 @@ int rma_record_capacity(int grids, int mode, float threshold, int depth_points) 
 }
 
 RmaWorkspace rma_workspace(int views, int height, int width, int grids, int mode, float threshold, int depth_points,
-                           int64_t bricks) {
+                           int64_t bricks, int64_t nvox) {
     RmaWorkspace w;
     w.rays = (int64_t)views * height * width;
     w.blocks = (w.rays + kRayThreads - 1) / kRayThreads;
@@ -40,7 +40,8 @@ RmaWorkspace rma_workspace(int views, int height, int width, int grids, int mode
     w.off_blk_off = o;  o = align256(o + sizeof(int64_t) * (size_t)w.blocks);
     w.off_rec_w = o;    o = align256(o + sizeof(float) * (size_t)w.rays * (size_t)w.cap);
     w.off_rec_i = o;    o = align256(o + sizeof(float) * (size_t)w.rays * (size_t)w.cap);
-    w.off_bricks = o;   o = align256(o + (size_t)bricks);
+    w.off_bricks = o;   o = align256(o + sizeof(float) * (size_t)bricks);
+    w.off_sigmoid = o;  o = align256(o + sizeof(float) * (size_t)nvox);
     w.total = o;
     return w;
 }
@@ -59,9 +60,15 @@ struct MarchParams {
     double *blk_wsum;
     float *rec_w, *rec_i;
     cnrma_rma_result *result;
-    const uint8_t *bricks;   // [nbx,nby,nbz] 1 = every voxel of the brick holds the same TSDF value
-    int nby, nbz;
+    const float *bricks;     // [nbx,nby,nbz] the sigmoid value shared by every voxel of the brick, NaN if mixed
+    int nbx, nby, nbz;
+    const float *sig;        // [nvox] sigmoid(-tsdf), written by tsdf_prepare_kernel
 };
+
+__device__ __forceinline__ float sigmoid_neg(float tv) {
+    // torch.sigmoid(-tsdf) = 1 / (1 + exp(tsdf)) (rm.py:757); the correctly rounded reciprocal is the IEEE quotient
+    return __frcp_rn(__fadd_rn(1.0f, expf(tv)));
+}
 
 // Per-ray constants of the position -> voxel id mapping.
 struct VoxelMap {
@@ -125,30 +132,39 @@ constexpr int kBrickShift = 2;                 // 4^3-voxel bricks
 constexpr int kBrick = 1 << kBrickShift;
 constexpr float kBrickMargin = 0.05f;          // voxels
 
-// one warp per brick: 64 voxels, two per lane
-__global__ void __launch_bounds__(256) tsdf_bricks_kernel(GridDev g, const float *__restrict__ tsdf, int nbx, int nby,
-                                                          int nbz, uint8_t *__restrict__ bricks) {
+// Pre-pass over the TSDF, one warp per 4^3 brick (two voxels per lane): tabulates s = sigmoid(-tsdf) per voxel
+// (so the march evaluates no exp: the table entry is produced by the same instructions, hence the same bits)
+// and records, per brick, the s shared by all its voxels (NaN when they differ).
+__global__ void __launch_bounds__(256) tsdf_prepare_kernel(GridDev g, const float *__restrict__ tsdf, int nbx, int nby,
+                                                           int nbz, float *__restrict__ sig,
+                                                           float *__restrict__ bricks) {
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (b >= nbx * nby * nbz) return;
     const int bz = b % nbz, bxy = b / nbz, by = bxy % nby, bx = bxy / nby;
     const int x0 = bx << kBrickShift, y0 = by << kBrickShift, z0 = bz << kBrickShift;
-    const uint32_t ref = __float_as_uint(__ldg(tsdf + (x0 * g.ny + y0) * g.nz + z0));
+    uint32_t first = 0;
     bool same = true;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const int v = lane + 32 * k;   // (x, y, z) = (v / 16, (v / 4) % 4, v % 4), clamped at the grid border
         const int x = min(x0 + (v >> 4), g.nx - 1), y = min(y0 + ((v >> 2) & 3), g.ny - 1), z = min(z0 + (v & 3), g.nz - 1);
-        same = same && (__float_as_uint(__ldg(tsdf + (x * g.ny + y) * g.nz + z)) == ref);
+        const int vox = (x * g.ny + y) * g.nz + z;
+        const float sv = sigmoid_neg(__ldg(tsdf + vox));
+        sig[vox] = sv;
+        const uint32_t bits = __float_as_uint(sv);
+        if (k == 0) first = __shfl_sync(0xffffffffu, bits, 0);
+        same = same && (bits == first);
     }
     same = __all_sync(0xffffffffu, same);
-    if (lane == 0) bricks[b] = (uint8_t)same;
+    if (lane == 0 && bricks != nullptr) bricks[b] = same ? __uint_as_float(first) : __int_as_float(0x7fc00000);
 }
 
-// Per-ray constants of the brick exit test: the ray leaves the brick of voxel c through the face
-// c_lo + face_a (in rounded voxel coordinates) at t_a = t0_a + (c_lo + face_a) * dt_a.
+// Per-ray constants of the brick exit test: in rounded voxel coordinates q_a(t) = (o_a - origin_a)/vs + t*d_a/vs,
+// so the ray reaches coordinate e at t = t0_a + e * dt_a.
 struct BrickRay {
-    float t0[3], dt[3], face[3];
+    float t0[3], dt[3];
+    bool fwd[3];        // direction of travel along the axis (axis-parallel rays never reach a face: dt = +-inf)
     float inv_t_one;
 };
 
@@ -157,26 +173,33 @@ __device__ __forceinline__ BrickRay make_brick_ray(const GridDev &g, const float
     const float org[3] = {g.ox, g.oy, g.oz};
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        const float inv_d = 1.0f / d[a];                     // +-inf for axis-parallel rays: that face is never reached
+        const float inv_d = 1.0f / d[a];
         b.t0[a] = (org[a] - o[a]) * inv_d;
         b.dt[a] = g.vs * inv_d;
-        // the brick spans voxel centres lo .. lo+kBrick-1, i.e. rounded coordinates in [lo-0.5, lo+kBrick-0.5]
-        b.face[a] = (inv_d >= 0.0f) ? ((float)kBrick - 0.5f - kBrickMargin) : (-0.5f + kBrickMargin);
+        b.fwd[a] = inv_d >= 0.0f;
     }
     b.inv_t_one = 1.0f / t_one;
     return b;
 }
 
-// Last step index that is certainly still inside the brick containing voxel (ix,iy,iz); -1 if none.
-__device__ __forceinline__ int brick_exit_step(const BrickRay &b, int ix, int iy, int iz) {
+// Last step index that is certainly still inside the (uniform) brick containing voxel (ix,iy,iz); -1 if none.
+// A brick spans voxel centres lo .. lo+kBrick-1, i.e. rounded coordinates [lo-0.5, lo+kBrick-0.5] clipped to the
+// grid; only positions inside the brick shrunk by kBrickMargin on every side count as inside.
+// (Chaining the jump through face-adjacent bricks of equal value was measured and loses: the per-lane hop loops
+// diverge and cost more than the samples they save -- 336 us vs 475 us on cfg 2.)
+__device__ __forceinline__ int brick_exit_step(const BrickRay &b, const GridDev &g, int ix, int iy, int iz) {
     const int c[3] = {ix, iy, iz};
+    const int dim[3] = {g.nx, g.ny, g.nz};
     float t_exit = 3.0e38f;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        const float edge = (float)(c[a] & ~(kBrick - 1)) + b.face[a];
-        t_exit = fminf(t_exit, b.t0[a] + edge * b.dt[a]);   // NaN (0 * inf, inf - inf) is ignored by fminf
+        const int lo = c[a] & ~(kBrick - 1);
+        const float edge = b.fwd[a] ? ((float)min(lo + kBrick, dim[a]) - 0.5f - kBrickMargin)
+                                    : ((float)lo - 0.5f + kBrickMargin);
+        t_exit = fminf(t_exit, b.t0[a] + edge * b.dt[a]);   // NaN (0 * inf, inf - inf: axis-parallel ray) is ignored
     }
-    const float steps = t_exit * b.inv_t_one - 1.0f;        // one more step of slack
+    // floor(t_exit / t_one): the margin (0.05 voxel >= 0.03 steps for any ray) dwarfs the ~1e-4-step fp32 error
+    const float steps = t_exit * b.inv_t_one;
     return (steps > 0.0f && steps < 1.0e9f) ? (int)steps : -1;
 }
 
@@ -187,11 +210,11 @@ __device__ __forceinline__ VoxelMap make_voxel_map(const GridDev &g) {
     return m;
 }
 
-__device__ __forceinline__ float sigmoid_neg(float tv) {
-    // torch.sigmoid(-tsdf) = 1 / (1 + exp(tsdf)) (rm.py:757); the correctly rounded reciprocal is the IEEE quotient
-    return __frcp_rn(__fadd_rn(1.0f, expf(tv)));
-}
 
+// Per-CTA totals: kept rows (the fill kernel works on the same blocks of kRayThreads consecutive rays) and the sum
+// of the kept weights (double, fixed shape -> deterministic).
+// (Mapping CTAs to 32x8-pixel tiles with 8x4-pixel warps instead of 256 consecutive rays was measured: no gain,
+// 336 -> 350 us on cfg 2 plus an extra block-count kernel, so rays stay in flat order.)
 template <int BLOCK>
 __device__ __forceinline__ void block_totals(int kept, double wsum, int32_t *blk_rows, double *blk_wsum) {
     __shared__ int s_rows[BLOCK / kWarp];
@@ -245,31 +268,30 @@ __global__ void __launch_bounds__(kRayThreads) march_neus_kernel(const __grid_co
         const int n_steps = ray_is_finite(o, d) ? p.N : -1;   // non-finite rays keep nothing (see sample_voxel)
 
         float T = 1.0f;
-        float tv_cur = 1.0f, s_cur = 0.0f;   // TSDF value / sigmoid of the current sample (set at i == 0)
+        float s_cur = 0.0f;   // sigmoid(-tsdf) of the current sample (set at i == 0)
+        const float s_out = sigmoid_neg(1.0f);   // samples outside the grid read tsdf = 1.0 (rm.py:744)
         int vox_cur = -1;
         bool entered = false;
         int overflow = 0;
         for (int i = 0; i <= n_steps; ++i) {
             int vox_next = -1;
             int skip_to = -1;
-            float tv_next = tv_cur;   // i == N: last sample repeated (rm.py:758)
+            float s_next = s_cur;   // i == N: last sample repeated (rm.py:758); same voxel -> same value
             if (i < p.N) {
                 int ix, iy, iz;
                 vox_next = sample_voxel(p.g, vm, o, d, __fmul_rn((float)i, p.t_one), ix, iy, iz);
-                // samples outside the grid read tsdf = 1.0 (rm.py:744); same voxel -> same value
                 if (i == 0 || vox_next != vox_cur) {
-                    tv_next = (vox_next >= 0) ? __ldg(p.tsdf + vox_next) : 1.0f;
+                    s_next = (vox_next >= 0) ? __ldg(p.sig + vox_next) : s_out;
                     if (can_skip && vox_next >= 0) {
                         const int brick = ((ix >> kBrickShift) * p.nby + (iy >> kBrickShift)) * p.nbz + (iz >> kBrickShift);
                         if (brick != last_brick) {
                             last_brick = brick;
-                            if (__ldg(p.bricks + brick)) skip_to = brick_exit_step(br, ix, iy, iz);
+                            if (__ldg(p.bricks + brick) == s_next)   // uniform brick (NaN marks mixed ones)
+                                skip_to = brick_exit_step(br, p.g, ix, iy, iz);
                         }
                     }
                 }
             }
-            float s_next = s_cur;
-            if (i == 0 || tv_next != tv_cur) s_next = sigmoid_neg(tv_next);
             if (i > 0 && (s_next != s_cur || keep_zero)) {
                 float a = __fdiv_rn(__fsub_rn(s_cur, s_next), s_cur);
                 a = (a < 0.0f) ? 0.0f : a;   // clamp(min=0), NaN-propagating like torch
@@ -292,10 +314,9 @@ __global__ void __launch_bounds__(kRayThreads) march_neus_kernel(const __grid_co
             // left it is never re-entered, and samples outside are never kept
             if (entered && vox_next < 0) break;
             entered = entered || (vox_next >= 0);
-            tv_cur = tv_next;
             s_cur = s_next;
             vox_cur = vox_next;
-            // samples i+1 .. skip_to all lie in this uniform brick: they read tv_cur, so alpha == 0 and nothing
+            // samples i+1 .. skip_to all lie in this uniform brick: they read s_cur, so alpha == 0 and nothing
             // changes; resume with sample skip_to + 1 (never past the repeated last sample)
             if (skip_to > i) i = min(skip_to, p.N - 1);
         }
@@ -719,19 +740,23 @@ cudaError_t run_march(const GridDev &g, const float *pinv, int V, int H, int W, 
     p.rec_i = reinterpret_cast<float *>(base + ws.off_rec_i);
     p.result = result;
     p.bricks = nullptr;
-    p.nby = p.nbz = 0;
+    p.nbx = p.nby = p.nbz = 0;
     cudaError_t err = cudaMemsetAsync(result, 0, sizeof(cnrma_rma_result), stream);
     if (err != cudaSuccess) return err;
-    if (mode == CNRMA_MARCH_NEUS && thr > 0.0f) {
+    p.sig = nullptr;
+    if (mode == CNRMA_MARCH_NEUS) {
         const int nbx = (g.nx + kBrick - 1) >> kBrickShift;
+        p.nbx = nbx;
         p.nby = (g.ny + kBrick - 1) >> kBrickShift;
         p.nbz = (g.nz + kBrick - 1) >> kBrickShift;
-        uint8_t *bricks = reinterpret_cast<uint8_t *>(base + ws.off_bricks);
+        float *bricks = (thr > 0.0f) ? reinterpret_cast<float *>(base + ws.off_bricks) : nullptr;
+        float *sig = reinterpret_cast<float *>(base + ws.off_sigmoid);
         const int nb = nbx * p.nby * p.nbz;
-        tsdf_bricks_kernel<<<(nb + 7) / 8, 256, 0, stream>>>(g, tsdf, nbx, p.nby, p.nbz, bricks);
+        tsdf_prepare_kernel<<<(nb + 7) / 8, 256, 0, stream>>>(g, tsdf, nbx, p.nby, p.nbz, sig, bricks);
         err = cudaGetLastError();
         if (err != cudaSuccess) return err;
         p.bricks = bricks;
+        p.sig = sig;
     }
     if (mode == CNRMA_MARCH_DEPTH)
         march_depth_kernel<<<(unsigned)ws.blocks, kRayThreads, 0, stream>>>(p);
@@ -771,11 +796,20 @@ static cudaError_t launch_fill(FillParams &p, int dtype, const void *const *view
                          reinterpret_cast<uintptr_t>(p.rows) % 4 == 0;
         if (tma) {
             const size_t smem = (size_t)(kRayThreads / kWarp) * kStageBytes;
+            static thread_local int attr_dev[2] = {-1, -1};   // dynamic-smem opt-in done once per device
+            int dev = 0;
+            cudaGetDevice(&dev);
             if (dtype == CNRMA_BF16) {
-                cudaFuncSetAttribute(fill_rows_tma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (attr_dev[1] != dev) {
+                    cudaFuncSetAttribute(fill_rows_tma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    attr_dev[1] = dev;
+                }
                 fill_rows_tma_kernel<__nv_bfloat16><<<blocks, kRayThreads, smem, stream>>>(p);
             } else {
-                cudaFuncSetAttribute(fill_rows_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (attr_dev[0] != dev) {
+                    cudaFuncSetAttribute(fill_rows_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    attr_dev[0] = dev;
+                }
                 fill_rows_tma_kernel<float><<<blocks, kRayThreads, smem, stream>>>(p);
             }
         } else if (dtype == CNRMA_BF16) {

@@ -303,23 +303,35 @@ def _march(fs, b, P_scaled_b, tsdf_b, grid, voxel_dim, voxel_size, grids, mode, 
     return m
 
 
+_pinned_results = {}
+
+
 def _read_result(m):
-    """The one host sync of the path: M (and the weight sum) back to the host."""
-    raw = bytes(m.result.cpu().numpy().tobytes())
-    res = _lib.RmaResult.from_buffer_copy(raw)
+    """The one host sync of the path: M (and the weight sum) back to the host, through a pinned staging buffer
+    and an event so that only this copy is waited for."""
+    dev = m.result.device
+    slot = _pinned_results.get(dev)
+    if slot is None:
+        slot = (torch.empty(C.sizeof(_lib.RmaResult), dtype=torch.uint8, pin_memory=True), torch.cuda.Event())
+        _pinned_results[dev] = slot
+    host, event = slot
+    host.copy_(m.result, non_blocking=True)
+    event.record(torch.cuda.current_stream(dev))
+    event.synchronize()
+    res = _lib.RmaResult.from_buffer_copy(host.numpy().tobytes())
     if res.overflow:
         raise CnrmaError(f"{res.overflow} rays exceeded the per-ray record capacity")
     return res
 
 
-def _fill(fs, b, m, grid, rows_host, normalize, mean_tensor=None):
+def _fill(fs, b, m, grid, rows_host, normalize, mean_tensor=None, desc=None):
     lib = _lib.load()
     device = fs.device
     cols = fs.C + (3 if normalize else 4)
     rows = torch.empty((rows_host, cols), dtype=torch.float32, device=device)
     if rows_host == 0:
         return rows
-    desc = fs.descriptor(b)
+    desc = desc if desc is not None else fs.descriptor(b)
     mean_ptr = C.c_void_p(mean_tensor.data_ptr()) if mean_tensor is not None else None
     _lib.check(lib.cnrma_rma_fill(C.byref(grid), C.c_void_p(m.pinv.data_ptr()), C.byref(desc), m.grids, m.t_one,
                                   m.mode, m.threshold, m.depth_points, C.c_void_p(m.workspace.data_ptr()),
@@ -360,10 +372,11 @@ def rma_points(projections, features, tsdf, voxel_dim, voxel_size, origin, strid
         for b in range(fs.B):
             m = _march(fs, b, P_scaled[:, b], tsdf[b, 0], grid, voxel_dim, voxel_size, grids, mode, threshold,
                        depth_points)
+            desc = fs.descriptor(b)          # host work done while the march runs, before the sync below
             res = _read_result(m)
             # view-sharded callers replace the local mean weight by the all-reduced one (distributed.py)
             mean_t = mean_hook(res.weight_sum, res.rows, device) if (mean_hook and normalize) else None
-            out.append(_fill(fs, b, m, grid, int(res.rows), normalize, mean_t))
+            out.append(_fill(fs, b, m, grid, int(res.rows), normalize, mean_t, desc))
             stats.append(dict(rows=int(res.rows), weight_sum=float(res.weight_sum), mean=float(res.mean)))
     return (out, stats) if return_stats else out
 

@@ -177,7 +177,7 @@ def test_golden_stateful_mirror(cn, golden):
 # against the oracle on seeded synthetic scenes
 # --------------------------------------------------------------------------------------------------
 
-SCENES = [("tiny", 0), ("small", 1), ("small", 2), ("cfg1", 0)]
+SCENES = [("tiny", 0), ("small", 1), ("small", 2), ("odd", 3), ("room40", 4), ("cfg1", 0)]
 
 
 @pytest.fixture(scope="module", params=SCENES, ids=lambda p: f"{p[0]}-s{p[1]}")
