@@ -37,7 +37,19 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-views", type=int, default=0, help="views in the CPU sample (0 = auto)")
     ap.add_argument("--stage", default="both", choices=["both", "a", "b"], help="profiling aid: run one stage only")
+    ap.add_argument("--mode", default="scene-dp", choices=["scene-dp", "view-sharded"],
+                    help="N>1: independent scenes per GPU (default) or ONE scene with its views sharded + one all-reduce")
     return ap.parse_args()
+
+
+def load_traffic(config):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the main kernels from the committed
+    `ncu --set full` capture of this same command (profiles/traffic.json); {} if the config was not profiled."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get(config, {})
+    return {}
 
 
 def load_peaks():
@@ -199,6 +211,9 @@ def main():
     cn.load()
 
     hbm_peak, peak_src = load_peaks()
+    if args.mode == "view-sharded":
+        run_view_sharded(args, cn, dev, rank, world)
+        return
     sc = cn.synthetic.make_scene(args.config, seed=rank, with_features=False)
     feats = cn.synthetic.device_features(sc, dev, channels_last=True)           # [V,1,C,H,W] logical
     if sc.meta.get("dtype") == "bf16":
@@ -279,19 +294,23 @@ def main():
     bytes_fill = m_rows * (3 + C) * 4 + V * H * W * C * esz + m_rows * 8 + V * H * W * 4
     kernels = {
         "aggregate_views_kernel": {"ms": ms_a, "bytes": bytes_a, "gbs": bytes_a / ms_a / 1e6 if ms_a else None},
-        "march_neus_kernel+scan": {"ms": ms_march, "ray_steps": sc.ray_steps,
-                                   "ray_steps_per_s": sc.ray_steps / ms_march * 1e3 if ms_march else None},
-        "fill_rows_kernel(+host sync)": {"ms": ms_fill, "bytes": bytes_fill,
-                                         "gbs": bytes_fill / ms_fill / 1e6 if ms_fill else None},
+        "tsdf_prepare+march_neus+scan_blocks": {"ms": ms_march, "ray_steps": sc.ray_steps,
+                                                "ray_steps_per_s": sc.ray_steps / ms_march * 1e3 if ms_march else None},
+        "fill_rows_tma_kernel(+host read of M)": {"ms": ms_fill, "bytes": bytes_fill,
+                                                  "gbs": bytes_fill / ms_fill / 1e6 if ms_fill else None},
     }
+    traffic = load_traffic(args.config)
     if ms_fill >= ms_a:
-        dom, ach, dbytes = "fill_rows_kernel", kernels["fill_rows_kernel(+host sync)"]["gbs"], bytes_fill
+        dom, ach, dbytes = "fill_rows_tma_kernel", kernels["fill_rows_tma_kernel(+host read of M)"]["gbs"], bytes_fill
     else:
         dom, ach, dbytes = "aggregate_views_kernel", kernels["aggregate_views_kernel"]["gbs"], bytes_a
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                "frac": (ach / hbm_peak) if ach else None, "traffic": None, "peak_source": peak_src,
+                "frac": (ach / hbm_peak) if ach else None, "traffic": traffic.get(dom), "peak_source": peak_src,
                 "algorithmic_bytes": dbytes,
-                "stage_a_frac": kernels["aggregate_views_kernel"]["gbs"] / hbm_peak if ms_a else None}
+                "timing": "CUDA events on the launch stream around the phase, inside the timed region (includes the "
+                          "launch / host-sync gaps of the phase)",
+                "stage_a_frac": kernels["aggregate_views_kernel"]["gbs"] / hbm_peak if ms_a else None,
+                "stage_a_traffic": traffic.get("aggregate_views_kernel")}
 
     value = world * sc.voxel_views / (ms_step * 1e-3)
 
@@ -320,9 +339,52 @@ def main():
         "ray_steps_per_s": world * sc.ray_steps / (ms_step * 1e-3),
         "stage_ms": {"stage_a": ms_a, "march": ms_march, "fill": ms_fill},
         "kernels": kernels, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
-        "gpu_launches": 4 * args.steps if args.stage == "both" else (1 if args.stage == "a" else 3) * args.steps,
+        "gpu_launches": (5 if args.stage == "both" else (1 if args.stage == "a" else 4)) * args.steps,
     }
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_view_sharded(args, cn, dev, rank, world):
+    """BASELINE config 4 style: ONE scene, views sharded over the ranks, dense Stage A sums + counts combined by one
+    NCCL all-reduce (strong scaling; `value` = the scene's voxel*views / max-over-ranks time)."""
+    import torch
+    import torch.distributed as dist
+    from cnrma_b200 import distributed as D
+    sc = cn.synthetic.make_scene(args.config, seed=0, with_features=False)
+    lo, hi = D.view_shard(sc.views, rank, world)
+    full = cn.synthetic.device_features(sc, dev, channels_last=True)      # same seed on every rank
+    feats = full[lo:hi]
+    proj = torch.from_numpy(sc.projections).to(dev).unsqueeze(1)[lo:hi]
+    del full
+    call = lambda: D.aggregate_views_sharded(proj, feats, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
+    for _ in range(max(args.warmup, 3)):
+        call()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        call()
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms /= args.steps
+    if rank == 0:
+        nbytes = sc.nvox * (sc.channels + 1) * 4
+        print(json.dumps({
+            "metric": "voxel_views_per_s", "value": sc.voxel_views / (ms * 1e-3), "unit": "voxel*views/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.config, sc) + " -- Stage A only, views sharded",
+                       "parallelism": f"view-shard{world} + 1 all-reduce of {nbytes / 1e6:.0f} MB"},
+            "scenes_per_s": 1e3 / ms, "gpu_launches": 2 * args.steps}))
     if world > 1:
         dist.destroy_process_group()
 

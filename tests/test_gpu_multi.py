@@ -1,0 +1,64 @@
+"""GPU, >= 2 devices (skipped otherwise): the view-sharded paths over real NCCL against the single-GPU result.
+Run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import cnrma_b200 as cn
+    from cnrma_b200 import distributed as D
+    sc = cn.synthetic.make_scene("small", seed=21)
+    lo, hi = D.view_shard(sc.views, rank, world)
+    f = torch.from_numpy(sc.features).to(dev).unsqueeze(1).permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+    p = torch.from_numpy(sc.projections).to(dev).unsqueeze(1)
+    t = torch.from_numpy(sc.tsdf).to(dev)[None, None]
+    args = (sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
+    vol, cnt, valid = D.aggregate_views_sharded(p[lo:hi], f[lo:hi], *args)
+    wsum, wtot = D.dense_rma_sharded(p[lo:hi], f[lo:hi], t, *args, grids=sc.grids, threshold=0.05)
+    pts = D.rma_points_sharded(p[lo:hi], f[lo:hi], t, *args, grids=sc.grids, threshold=0.05)[0]
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([pts.shape[0]], dtype=torch.int64, device=dev))
+    if rank == 0:
+        # single-GPU results on the same device
+        v1, c1, _ = cn.aggregate_views(p, f, *args)
+        s1, t1 = cn.dense_rma(p, f, t, *args, grids=sc.grids, threshold=0.05)
+        p1 = cn.rma_points(p, f, t, *args, grids=sc.grids, threshold=0.05)[0]
+        ret["cnt_equal"] = bool(torch.equal(cnt.view(-1), c1.view(-1).float()))
+        ret["vol_err"] = float((vol - v1).abs().max() / v1.abs().max())
+        ret["wtot_err"] = float((wtot - t1).abs().max() / t1.abs().max())
+        ret["wsum_err"] = float((wsum - s1).abs().max() / s1.abs().max())
+        n0 = int(sizes[0])
+        ret["rows_total"] = int(sum(int(s) for s in sizes)) == p1.shape[0]
+        ret["pts_err"] = float((pts - p1[:n0]).abs().max() / p1.abs().max())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_view_sharded_over_nccl():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    port = 29600 + (os.getpid() % 1000)
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+        got = dict(ret)
+    assert got["cnt_equal"]
+    assert got["vol_err"] <= 1e-5
+    assert got["wtot_err"] <= 1e-5 and got["wsum_err"] <= 1e-5
+    assert got["rows_total"]
+    assert got["pts_err"] <= 1e-5
