@@ -40,7 +40,8 @@ RmaWorkspace rma_workspace(int views, int height, int width, int grids, int mode
     w.off_blk_off = o;  o = align256(o + sizeof(int64_t) * (size_t)w.blocks);
     w.off_rec_w = o;    o = align256(o + sizeof(float) * (size_t)w.rays * (size_t)w.cap);
     w.off_rec_i = o;    o = align256(o + sizeof(float) * (size_t)w.rays * (size_t)w.cap);
-    w.off_bricks = o;   o = align256(o + sizeof(float) * (size_t)bricks);
+    (void)bricks;
+    w.off_bricks = o;   o = align256(o + 2 * (size_t)nvox);   // two uint8 distance fields (ping-pong)
     w.off_sigmoid = o;  o = align256(o + sizeof(float) * (size_t)nvox);
     w.total = o;
     return w;
@@ -60,8 +61,7 @@ struct MarchParams {
     double *blk_wsum;
     float *rec_w, *rec_i;
     cnrma_rma_result *result;
-    const float *bricks;     // [nbx,nby,nbz] the sigmoid value shared by every voxel of the brick, NaN if mixed
-    int nbx, nby, nbz;
+    const uint8_t *dist;     // [nvox] Chebyshev distance (capped) to the nearest voxel of another sigmoid value
     const float *sig;        // [nvox] sigmoid(-tsdf), written by tsdf_prepare_kernel
 };
 
@@ -121,86 +121,64 @@ __device__ __forceinline__ bool ray_is_finite(const float o[3], const float d[3]
     return isfinite(o[0] + o[1] + o[2]) && isfinite(d[0] + d[1] + d[2]);
 }
 
-// ---- uniform-brick skipping ------------------------------------------------------------------------------
+// ---- empty-space skipping ----------------------------------------------------------------------------------
 // The TSDF the reference marches through is piecewise constant over large regions (free space and unobserved
 // space are set to +-0.999 by the coarse-to-fine head, atlas_head.py:47).  Consecutive samples that read the
-// same value have alpha == 0 exactly, so a run of samples inside a brick whose voxels all hold one value
-// changes neither the transmittance nor (for thr > 0) the kept set, and can be jumped over.  The jump is
-// conservative: only steps whose position lies inside the brick shrunk by kBrickMargin voxels on every side
-// (far more than the fp32 error of o + d*t) are skipped, and the step after the jump is marched normally.
-constexpr int kBrickShift = 2;                 // 4^3-voxel bricks
-constexpr int kBrick = 1 << kBrickShift;
-constexpr float kBrickMargin = 0.05f;          // voxels
+// same value have alpha == 0 exactly: they change neither the transmittance nor (for thr > 0) the kept set.
+// A pre-pass tabulates s = sigmoid(-tsdf) per voxel and a capped Chebyshev distance field D: D(c) = k means every
+// voxel within L-infinity distance k of c holds the same s as c (voxels next to a different value, and the grid
+// border, have D = 0).  A sample that rounds to voxel c sits within 0.5 voxel of its centre, so the next
+// n = floor((k - margin) / max_a |step_a|) samples stay within k + 0.5 - margin of the centre, round to voxels
+// inside that cube and read the same s: the march jumps over them.  ("step" is the per-sample advance in voxel
+// units; margin = 0.05 voxel dwarfs the ~1e-5 voxel fp32 error of o + d*t.)
+constexpr int kDistCap = 15;
+constexpr float kSkipMargin = 0.05f;
 
-// Pre-pass over the TSDF, one warp per 4^3 brick (two voxels per lane): tabulates s = sigmoid(-tsdf) per voxel
-// (so the march evaluates no exp: the table entry is produced by the same instructions, hence the same bits)
-// and records, per brick, the s shared by all its voxels (NaN when they differ).
-__global__ void __launch_bounds__(256) tsdf_prepare_kernel(GridDev g, const float *__restrict__ tsdf, int nbx, int nby,
-                                                           int nbz, float *__restrict__ sig,
-                                                           float *__restrict__ bricks) {
-    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (b >= nbx * nby * nbz) return;
-    const int bz = b % nbz, bxy = b / nbz, by = bxy % nby, bx = bxy / nby;
-    const int x0 = bx << kBrickShift, y0 = by << kBrickShift, z0 = bz << kBrickShift;
-    uint32_t first = 0;
-    bool same = true;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const int v = lane + 32 * k;   // (x, y, z) = (v / 16, (v / 4) % 4, v % 4), clamped at the grid border
-        const int x = min(x0 + (v >> 4), g.nx - 1), y = min(y0 + ((v >> 2) & 3), g.ny - 1), z = min(z0 + (v & 3), g.nz - 1);
-        const int vox = (x * g.ny + y) * g.nz + z;
-        const float sv = sigmoid_neg(__ldg(tsdf + vox));
-        sig[vox] = sv;
-        const uint32_t bits = __float_as_uint(sv);
-        if (k == 0) first = __shfl_sync(0xffffffffu, bits, 0);
-        same = same && (bits == first);
-    }
-    same = __all_sync(0xffffffffu, same);
-    if (lane == 0 && bricks != nullptr) bricks[b] = same ? __uint_as_float(first) : __int_as_float(0x7fc00000);
+__global__ void __launch_bounds__(256) tsdf_sigmoid_kernel(const float *__restrict__ tsdf, int nvox,
+                                                           float *__restrict__ sig) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < nvox) sig[v] = sigmoid_neg(__ldg(tsdf + v));
 }
 
-// Per-ray constants of the brick exit test: in rounded voxel coordinates q_a(t) = (o_a - origin_a)/vs + t*d_a/vs,
-// so the ray reaches coordinate e at t = t0_a + e * dt_a.
-struct BrickRay {
-    float t0[3], dt[3];
-    bool fwd[3];        // direction of travel along the axis (axis-parallel rays never reach a face: dt = +-inf)
-    float inv_t_one;
-};
-
-__device__ __forceinline__ BrickRay make_brick_ray(const GridDev &g, const float o[3], const float d[3], float t_one) {
-    BrickRay b;
-    const float org[3] = {g.ox, g.oy, g.oz};
+// Pass 1 (along z, the contiguous axis): boundary test + 1-D distance.  A voxel is a boundary voxel when it lies on
+// the grid border or any of its 26 neighbours holds a different s.
+__device__ __forceinline__ bool is_boundary(const GridDev &g, const float *__restrict__ sig, int x, int y, int z) {
+    if (x == 0 || y == 0 || z == 0 || x == g.nx - 1 || y == g.ny - 1 || z == g.nz - 1) return true;
+    const uint32_t ref = __float_as_uint(__ldg(sig + (x * g.ny + y) * g.nz + z));
+    bool differs = false;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const float inv_d = 1.0f / d[a];
-        b.t0[a] = (org[a] - o[a]) * inv_d;
-        b.dt[a] = g.vs * inv_d;
-        b.fwd[a] = inv_d >= 0.0f;
-    }
-    b.inv_t_one = 1.0f / t_one;
-    return b;
+    for (int dx = -1; dx <= 1; ++dx)
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dz = -1; dz <= 1; ++dz)
+                differs = differs || (__float_as_uint(__ldg(sig + ((x + dx) * g.ny + (y + dy)) * g.nz + (z + dz))) != ref);
+    return differs;
 }
 
-// Last step index that is certainly still inside the (uniform) brick containing voxel (ix,iy,iz); -1 if none.
-// A brick spans voxel centres lo .. lo+kBrick-1, i.e. rounded coordinates [lo-0.5, lo+kBrick-0.5] clipped to the
-// grid; only positions inside the brick shrunk by kBrickMargin on every side count as inside.
-// (Chaining the jump through face-adjacent bricks of equal value was measured and loses: the per-lane hop loops
-// diverge and cost more than the samples they save -- 336 us vs 475 us on cfg 2.)
-__device__ __forceinline__ int brick_exit_step(const BrickRay &b, const GridDev &g, int ix, int iy, int iz) {
-    const int c[3] = {ix, iy, iz};
-    const int dim[3] = {g.nx, g.ny, g.nz};
-    float t_exit = 3.0e38f;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const int lo = c[a] & ~(kBrick - 1);
-        const float edge = b.fwd[a] ? ((float)min(lo + kBrick, dim[a]) - 0.5f - kBrickMargin)
-                                    : ((float)lo - 0.5f + kBrickMargin);
-        t_exit = fminf(t_exit, b.t0[a] + edge * b.dt[a]);   // NaN (0 * inf, inf - inf: axis-parallel ray) is ignored
+__global__ void __launch_bounds__(256) dist_boundary_kernel(GridDev g, const float *__restrict__ sig,
+                                                            uint8_t *__restrict__ out) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= g.nx * g.ny * g.nz) return;
+    const int z = v % g.nz, xy = v / g.nz, y = xy % g.ny, x = xy / g.ny;
+    out[v] = is_boundary(g, sig, x, y, z) ? 0 : kDistCap;
+}
+
+// Separable L-infinity distance transform: out(v) = min over |d| <= cap along `axis` of max(|d|, in(v + d)).
+__global__ void __launch_bounds__(256) dist_pass_kernel(GridDev g, int axis, const uint8_t *__restrict__ in,
+                                                        uint8_t *__restrict__ out) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= g.nx * g.ny * g.nz) return;
+    const int z = v % g.nz, xy = v / g.nz, y = xy % g.ny, x = xy / g.ny;
+    const int pos = (axis == 0) ? x : ((axis == 1) ? y : z);
+    const int n = (axis == 0) ? g.nx : ((axis == 1) ? g.ny : g.nz);
+    const int stride = (axis == 0) ? g.ny * g.nz : ((axis == 1) ? g.nz : 1);
+    int best = in[v];
+    for (int d = 1; d < best; ++d) {   // a neighbour at distance d can only help while d < best
+        if (pos - d >= 0) best = min(best, max(d, (int)in[v - d * stride]));
+        if (pos + d < n) best = min(best, max(d, (int)in[v + d * stride]));
     }
-    // floor(t_exit / t_one): the margin (0.05 voxel >= 0.03 steps for any ray) dwarfs the ~1e-4-step fp32 error
-    const float steps = t_exit * b.inv_t_one;
-    return (steps > 0.0f && steps < 1.0e9f) ? (int)steps : -1;
+    out[v] = (uint8_t)best;
 }
 
 __device__ __forceinline__ VoxelMap make_voxel_map(const GridDev &g) {
@@ -262,9 +240,10 @@ __global__ void __launch_bounds__(kRayThreads) march_neus_kernel(const __grid_co
         const VoxelMap vm = make_voxel_map(p.g);
         const bool keep_zero = !(p.thr > 0.0f);   // thr <= 0 (or NaN): zero weights pass `w >= thr` too
 
-        const BrickRay br = make_brick_ray(p.g, o, d, p.t_one);
-        const bool can_skip = !keep_zero && p.bricks != nullptr;
-        int last_brick = -1;
+        // samples the ray may jump per voxel of clearance: 1 / max_a |d_a * t_one / vs|
+        const float step_max = fmaxf(fmaxf(fabsf(d[0]), fabsf(d[1])), fabsf(d[2])) * p.t_one / p.g.vs;
+        const float inv_step = (step_max > 0.0f) ? 1.0f / step_max : 0.0f;
+        const bool can_skip = !keep_zero && p.dist != nullptr;
         const int n_steps = ray_is_finite(o, d) ? p.N : -1;   // non-finite rays keep nothing (see sample_voxel)
 
         float T = 1.0f;
@@ -278,18 +257,14 @@ __global__ void __launch_bounds__(kRayThreads) march_neus_kernel(const __grid_co
             int skip_to = -1;
             float s_next = s_cur;   // i == N: last sample repeated (rm.py:758); same voxel -> same value
             if (i < p.N) {
-                int ix, iy, iz;
-                vox_next = sample_voxel(p.g, vm, o, d, __fmul_rn((float)i, p.t_one), ix, iy, iz);
+                vox_next = sample_voxel(p.g, vm, o, d, __fmul_rn((float)i, p.t_one));
                 if (i == 0 || vox_next != vox_cur) {
                     s_next = (vox_next >= 0) ? __ldg(p.sig + vox_next) : s_out;
-                    if (can_skip && vox_next >= 0) {
-                        const int brick = ((ix >> kBrickShift) * p.nby + (iy >> kBrickShift)) * p.nbz + (iz >> kBrickShift);
-                        if (brick != last_brick) {
-                            last_brick = brick;
-                            if (__ldg(p.bricks + brick) == s_next)   // uniform brick (NaN marks mixed ones)
-                                skip_to = brick_exit_step(br, p.g, ix, iy, iz);
-                        }
-                    }
+                }
+                if (can_skip && vox_next >= 0) {
+                    // clearance k voxels -> the next floor((k - margin) / step) samples read the same value
+                    const int k = __ldg(p.dist + vox_next);
+                    if (k > 0) skip_to = i + (int)(((float)k - kSkipMargin) * inv_step);
                 }
             }
             if (i > 0 && (s_next != s_cur || keep_zero)) {
@@ -316,7 +291,7 @@ __global__ void __launch_bounds__(kRayThreads) march_neus_kernel(const __grid_co
             entered = entered || (vox_next >= 0);
             s_cur = s_next;
             vox_cur = vox_next;
-            // samples i+1 .. skip_to all lie in this uniform brick: they read s_cur, so alpha == 0 and nothing
+            // samples i+1 .. skip_to all round to voxels that hold s_cur, so alpha == 0 and nothing
             // changes; resume with sample skip_to + 1 (never past the repeated last sample)
             if (skip_to > i) i = min(skip_to, p.N - 1);
         }
@@ -739,24 +714,27 @@ cudaError_t run_march(const GridDev &g, const float *pinv, int V, int H, int W, 
     p.rec_w = reinterpret_cast<float *>(base + ws.off_rec_w);
     p.rec_i = reinterpret_cast<float *>(base + ws.off_rec_i);
     p.result = result;
-    p.bricks = nullptr;
-    p.nbx = p.nby = p.nbz = 0;
+    p.dist = nullptr;
+    p.sig = nullptr;
     cudaError_t err = cudaMemsetAsync(result, 0, sizeof(cnrma_rma_result), stream);
     if (err != cudaSuccess) return err;
-    p.sig = nullptr;
     if (mode == CNRMA_MARCH_NEUS) {
-        const int nbx = (g.nx + kBrick - 1) >> kBrickShift;
-        p.nbx = nbx;
-        p.nby = (g.ny + kBrick - 1) >> kBrickShift;
-        p.nbz = (g.nz + kBrick - 1) >> kBrickShift;
-        float *bricks = (thr > 0.0f) ? reinterpret_cast<float *>(base + ws.off_bricks) : nullptr;
+        const int nvox = g.nx * g.ny * g.nz;
+        const unsigned vb = (unsigned)((nvox + 255) / 256);
         float *sig = reinterpret_cast<float *>(base + ws.off_sigmoid);
-        const int nb = nbx * p.nby * p.nbz;
-        tsdf_prepare_kernel<<<(nb + 7) / 8, 256, 0, stream>>>(g, tsdf, nbx, p.nby, p.nbz, sig, bricks);
+        tsdf_sigmoid_kernel<<<vb, 256, 0, stream>>>(tsdf, nvox, sig);
+        p.sig = sig;
+        if (thr > 0.0f) {
+            uint8_t *d0 = reinterpret_cast<uint8_t *>(base + ws.off_bricks);
+            uint8_t *d1 = d0 + nvox;
+            dist_boundary_kernel<<<vb, 256, 0, stream>>>(g, sig, d0);
+            dist_pass_kernel<<<vb, 256, 0, stream>>>(g, 2, d0, d1);
+            dist_pass_kernel<<<vb, 256, 0, stream>>>(g, 1, d1, d0);
+            dist_pass_kernel<<<vb, 256, 0, stream>>>(g, 0, d0, d1);
+            p.dist = d1;
+        }
         err = cudaGetLastError();
         if (err != cudaSuccess) return err;
-        p.bricks = bricks;
-        p.sig = sig;
     }
     if (mode == CNRMA_MARCH_DEPTH)
         march_depth_kernel<<<(unsigned)ws.blocks, kRayThreads, 0, stream>>>(p);
@@ -868,7 +846,7 @@ cudaError_t run_expand(int64_t rays, int N, const void *workspace, const RmaWork
 
 namespace cnrma {
 int64_t rma_brick_count(const GridDev &g) {
-    return (int64_t)((g.nx + kBrick - 1) >> kBrickShift) * ((g.ny + kBrick - 1) >> kBrickShift) *
-           ((g.nz + kBrick - 1) >> kBrickShift);
+    (void)g;
+    return 0;   // the brick table was replaced by the per-voxel distance field (sized by nvox)
 }
 }  // namespace cnrma
