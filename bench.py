@@ -247,9 +247,10 @@ def main():
                          pinv=pinv)
             if ev:
                 ev[2].record()
-            res = F._read_result(m)              # the path's one host sync: M sizes the output
+            # fill is queued speculatively (row count of the previous scene + headroom) and the read-back of M,
+            # the path's one host sync, overlaps with it; see functional._march_and_fill
+            rows, res = F._march_and_fill(fs, 0, m, grid, True, None, ("bench", args.config), fill_desc)
             m_rows = int(res.rows)
-            rows = F._fill(fs, 0, m, grid, m_rows, True, None, fill_desc)
         elif ev:
             ev[2].record()
         if ev:

@@ -189,7 +189,8 @@ int cnrma_rma_march(const cnrma_grid *grid, const float *pinv, int views, int he
 // arguments (grids, mode, threshold, depth_points) the march call was given.
 static int fill_common(const cnrma_grid *grid, const float *pinv, const cnrma_features *features, int grids,
                        float t_one, int mode, float threshold, int depth_points, const void *workspace, int normalize,
-                       const float *mean, float *rows, int64_t row_stride, float *wsum, float *wtot, void *stream) {
+                       const float *mean, float *rows, int64_t row_stride, int64_t capacity, float *wsum, float *wtot,
+                       void *stream) {
     if (!grid_ok(grid) || !pinv || !workspace) return CNRMA_ERR_ARG;
     const int fs = features_ok(features, false);
     if (fs != CNRMA_OK) return fs;
@@ -199,7 +200,7 @@ static int fill_common(const cnrma_grid *grid, const float *pinv, const cnrma_fe
     const RmaWorkspace ws = rma_workspace(features->views, features->height, features->width, grids, mode, threshold,
                                           depth_points);
     const cudaError_t e = run_fill(to_dev(*grid), pinv, *features, t_one, mode, workspace, ws, normalize, mean, rows,
-                                   row_stride, wsum, wtot, static_cast<cudaStream_t>(stream));
+                                   row_stride, capacity, wsum, wtot, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
 }
 
@@ -207,15 +208,15 @@ int cnrma_rma_fill(const cnrma_grid *grid, const float *pinv, const cnrma_featur
                    int mode, float threshold, int depth_points, const void *workspace, const cnrma_rma_result *result,
                    int64_t rows_host, int normalize, const float *mean, float *rows, int64_t row_stride,
                    int64_t capacity, void *stream) {
-    if (!rows || !result || rows_host < 0) return CNRMA_ERR_ARG;
+    if (!rows || !result || capacity < 0) return CNRMA_ERR_ARG;
     if (!features) return CNRMA_ERR_ARG;
     const int cols = features->channels + (normalize ? 3 : 4);
     if (row_stride < cols) return CNRMA_ERR_ARG;
-    if (capacity < rows_host) return CNRMA_ERR_CAPACITY;
-    if (rows_host == 0) return CNRMA_OK;
+    if (rows_host >= 0 && capacity < rows_host) return CNRMA_ERR_CAPACITY;
+    if (rows_host == 0 || capacity == 0) return CNRMA_OK;
     const float *mean_ptr = mean ? mean : &result->mean;
     return fill_common(grid, pinv, features, grids, t_one, mode, threshold, depth_points, workspace, normalize,
-                       mean_ptr, rows, row_stride, nullptr, nullptr, stream);
+                       mean_ptr, rows, row_stride, capacity, nullptr, nullptr, stream);
 }
 
 int cnrma_rma_scatter(const cnrma_grid *grid, const float *pinv, const cnrma_features *features, int grids,
@@ -223,7 +224,7 @@ int cnrma_rma_scatter(const cnrma_grid *grid, const float *pinv, const cnrma_fea
                       float *wtot, void *stream) {
     if (!wsum || !wtot) return CNRMA_ERR_ARG;
     return fill_common(grid, pinv, features, grids, t_one, mode, threshold, depth_points, workspace, 0, nullptr,
-                       nullptr, 0, wsum, wtot, stream);
+                       nullptr, 0, 0, wsum, wtot, stream);
 }
 
 int cnrma_rma_expand(int views, int height, int width, int grids, float threshold, const void *workspace,

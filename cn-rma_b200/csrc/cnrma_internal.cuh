@@ -32,7 +32,7 @@ cudaError_t run_march(const GridDev &g, const float *pinv, int V, int H, int W, 
                       cnrma_rma_result *result, cudaStream_t stream);
 cudaError_t run_fill(const GridDev &g, const float *pinv, const cnrma_features &f, float t_one, int mode,
                      const void *workspace, const RmaWorkspace &ws, int normalize, const float *mean, float *rows,
-                     int64_t row_stride, float *wsum, float *wtot, cudaStream_t stream);
+                     int64_t row_stride, int64_t capacity, float *wsum, float *wtot, cudaStream_t stream);
 cudaError_t run_ray_parameters(const float *pinv, int V, int H, int W, float *o, float *d, cudaStream_t stream);
 cudaError_t run_expand(int64_t rays, int N, const void *workspace, const RmaWorkspace &ws, float *weights,
                        uint8_t *keep, cudaStream_t stream);

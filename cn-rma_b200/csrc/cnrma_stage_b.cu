@@ -413,6 +413,7 @@ struct FillParams {
     const float *mean;
     float *rows;
     int64_t row_stride;
+    int64_t capacity;     // rows the output buffer holds: rows beyond it are dropped (speculative launches)
     float *wsum, *wtot;   // scatter variant
     const void *views[kMaxViewsPerLaunch];
     int view_base;        // first view of this launch
@@ -485,7 +486,7 @@ __global__ void __launch_bounds__(kRayThreads) fill_rows_kernel(const __grid_con
             const int nk = min(32, cnt - k0);
             float wk = 0.0f;       // weight that multiplies the features of this lane's record
             int64_t vox = -1;      // scatter target
-            if (lane < nk) {
+            if (lane < nk && (SCATTER || off + k0 + lane < p.capacity)) {
                 const float w = __ldg(p.rec_w + (int64_t)(k0 + lane) * p.rays + ray);
                 const float fi = __ldg(p.rec_i + (int64_t)(k0 + lane) * p.rays + ray);
                 float pos[3];
@@ -524,6 +525,7 @@ __global__ void __launch_bounds__(kRayThreads) fill_rows_kernel(const __grid_con
                 for (int k = 0; k < nk; ++k) {
                     const float wn = __shfl_sync(0xffffffffu, wk, k);
                     if (!SCATTER) {
+                        if (off + k0 + k >= p.capacity) break;
                         float *dst = p.rows + (off + k0 + k) * p.row_stride + col0;
 #pragma unroll
                         for (int j = 0; j < kFillRegs; ++j) {
@@ -600,7 +602,7 @@ __global__ void __launch_bounds__(kRayThreads) fill_rows_tma_kernel(const __grid
             f[j] = (c < p.C) ? load_feat<T>(feat + c) : 0.0f;
         }
         for (int k0 = 0; k0 < cnt; k0 += 32) {
-            const int nk = min(32, cnt - k0);
+            const int nk = (int)min((int64_t)min(32, cnt - k0), max((int64_t)0, p.capacity - (off + k0)));   // rows that fit
             float wk = 0.0f, wraw = 0.0f, pos[3] = {0.0f, 0.0f, 0.0f};
             if (lane < nk) {
                 wraw = __ldg(p.rec_w + (int64_t)(k0 + lane) * p.rays + ray);
@@ -803,7 +805,7 @@ static cudaError_t launch_fill(FillParams &p, int dtype, const void *const *view
 
 cudaError_t run_fill(const GridDev &g, const float *pinv, const cnrma_features &f, float t_one, int mode,
                      const void *workspace, const RmaWorkspace &ws, int normalize, const float *mean, float *rows,
-                     int64_t row_stride, float *wsum, float *wtot, cudaStream_t stream) {
+                     int64_t row_stride, int64_t capacity, float *wsum, float *wtot, cudaStream_t stream) {
     const unsigned char *base = static_cast<const unsigned char *>(workspace);
     FillParams p;
     p.g = g;
@@ -821,6 +823,7 @@ cudaError_t run_fill(const GridDev &g, const float *pinv, const cnrma_features &
     p.mean = mean;
     p.rows = rows;
     p.row_stride = row_stride;
+    p.capacity = capacity;
     p.wsum = wsum;
     p.wtot = wtot;
     p.view_base = 0;

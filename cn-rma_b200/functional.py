@@ -300,6 +300,8 @@ def _march(fs, b, P_scaled_b, tsdf_b, grid, voxel_dim, voxel_size, grids, mode, 
                                    C.c_void_p(tsdf_b.data_ptr()), m.grids, m.t_one, m.mode, m.threshold,
                                    m.depth_points, C.c_void_p(m.workspace.data_ptr()), nbytes.value,
                                    C.c_void_p(m.result.data_ptr()), _stream(device)), "cnrma_rma_march")
+    m.done = torch.cuda.Event()
+    m.done.record(torch.cuda.current_stream(device))
     return m
 
 
@@ -307,16 +309,21 @@ _pinned_results = {}
 
 
 def _read_result(m):
-    """The one host sync of the path: M (and the weight sum) back to the host, through a pinned staging buffer
-    and an event so that only this copy is waited for."""
+    """The one host sync of the path: M (and the weight sum) back to the host.  The copy runs on a side stream
+    that waits only for the march / scan kernels (event recorded by _march), through a pinned staging buffer, so
+    a fill kernel queued speculatively behind the march does not delay it."""
     dev = m.result.device
     slot = _pinned_results.get(dev)
     if slot is None:
-        slot = (torch.empty(C.sizeof(_lib.RmaResult), dtype=torch.uint8, pin_memory=True), torch.cuda.Event())
+        slot = (torch.empty(C.sizeof(_lib.RmaResult), dtype=torch.uint8, pin_memory=True), torch.cuda.Event(),
+                torch.cuda.Stream(device=dev))
         _pinned_results[dev] = slot
-    host, event = slot
-    host.copy_(m.result, non_blocking=True)
-    event.record(torch.cuda.current_stream(dev))
+    host, event, side = slot
+    side.wait_event(m.done)
+    with torch.cuda.stream(side):
+        host.copy_(m.result, non_blocking=True)
+        event.record(side)
+    m.result.record_stream(side)
     event.synchronize()
     res = _lib.RmaResult.from_buffer_copy(host.numpy().tobytes())
     if res.overflow:
@@ -324,20 +331,46 @@ def _read_result(m):
     return res
 
 
-def _fill(fs, b, m, grid, rows_host, normalize, mean_tensor=None, desc=None):
+def _fill(fs, b, m, grid, rows_host, normalize, mean_tensor=None, desc=None, capacity=None):
+    """Launches the fill kernel.  With `capacity` and rows_host = -1 the launch is speculative: it happens before M
+    is known on the host, into a buffer of `capacity` rows (rows beyond it are dropped by the kernel)."""
     lib = _lib.load()
     device = fs.device
     cols = fs.C + (3 if normalize else 4)
-    rows = torch.empty((rows_host, cols), dtype=torch.float32, device=device)
-    if rows_host == 0:
+    cap = rows_host if capacity is None else capacity
+    rows = torch.empty((cap, cols), dtype=torch.float32, device=device)
+    if cap == 0:
         return rows
     desc = desc if desc is not None else fs.descriptor(b)
     mean_ptr = C.c_void_p(mean_tensor.data_ptr()) if mean_tensor is not None else None
     _lib.check(lib.cnrma_rma_fill(C.byref(grid), C.c_void_p(m.pinv.data_ptr()), C.byref(desc), m.grids, m.t_one,
                                   m.mode, m.threshold, m.depth_points, C.c_void_p(m.workspace.data_ptr()),
                                   C.c_void_p(m.result.data_ptr()), rows_host, 1 if normalize else 0, mean_ptr,
-                                  C.c_void_p(rows.data_ptr()), cols, rows_host, _stream(device)), "cnrma_rma_fill")
+                                  C.c_void_p(rows.data_ptr()), cols, cap, _stream(device)), "cnrma_rma_fill")
     return rows
+
+
+# rows kept by the previous call with the same shapes: lets the fill kernel be queued before M has been read back
+_rows_hint = {}
+
+
+def _march_and_fill(fs, b, m, grid, normalize, mean_hook, key, desc=None):
+    """march result -> rows.  If an earlier call with the same shapes tells how many rows to expect, the fill is
+    launched speculatively into a buffer with 6 % headroom and the read-back of M (the path's one host sync)
+    overlaps with it; otherwise (first call, view-sharded mean, or the rare overflow) M is read first."""
+    device = fs.device
+    desc = desc if desc is not None else fs.descriptor(b)
+    hint = _rows_hint.get(key)
+    rows = None
+    if hint and mean_hook is None:
+        rows = _fill(fs, b, m, grid, -1, normalize, None, desc, capacity=hint)
+    res = _read_result(m)
+    n = int(res.rows)
+    if rows is None or n > rows.shape[0]:
+        mean_t = mean_hook(res.weight_sum, res.rows, device) if (mean_hook and normalize) else None
+        rows = _fill(fs, b, m, grid, n, normalize, mean_t, desc)
+    _rows_hint[key] = n + n // 16 + 1024
+    return rows[:n], res
 
 
 def _check_mode(mode, threshold, depth_points):
@@ -372,11 +405,11 @@ def rma_points(projections, features, tsdf, voxel_dim, voxel_size, origin, strid
         for b in range(fs.B):
             m = _march(fs, b, P_scaled[:, b], tsdf[b, 0], grid, voxel_dim, voxel_size, grids, mode, threshold,
                        depth_points)
-            desc = fs.descriptor(b)          # host work done while the march runs, before the sync below
-            res = _read_result(m)
             # view-sharded callers replace the local mean weight by the all-reduced one (distributed.py)
-            mean_t = mean_hook(res.weight_sum, res.rows, device) if (mean_hook and normalize) else None
-            out.append(_fill(fs, b, m, grid, int(res.rows), normalize, mean_t, desc))
+            key = (device.index, b, fs.V, fs.C, fs.H, fs.W, tuple(int(v) for v in voxel_dim), int(grids), mode,
+                   threshold, depth_points, bool(normalize))
+            rows, res = _march_and_fill(fs, b, m, grid, normalize, mean_hook, key)
+            out.append(rows)
             stats.append(dict(rows=int(res.rows), weight_sum=float(res.weight_sum), mean=float(res.mean)))
     return (out, stats) if return_stats else out
 

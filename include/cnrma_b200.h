@@ -158,8 +158,10 @@ int cnrma_rma_march(const cnrma_grid *grid, const float *pinv, int views, int he
  *   rows        f32 [M, row_stride]; columns  normalize ? [x,y,z, feat*w/mean] : [x,y,z,w, feat]
  *   mean        device float used as the divisor when normalize != 0; NULL = result->mean of the march
  *               (a view-sharded caller passes the all-reduced mean here)
- *   capacity    rows the buffer can hold; CNRMA_ERR_CAPACITY is returned (host-side check against
- *               rows_host) if smaller than M
+ *   capacity    rows the buffer can hold; rows beyond it are not written
+ *   rows_host   M as read back from result->rows: CNRMA_ERR_CAPACITY if capacity < rows_host.  Pass -1 to launch
+ *               speculatively BEFORE reading M (the kernel takes its offsets from the workspace, not from M): the
+ *               caller then compares result->rows with capacity afterwards and repeats the call if it did not fit
  * grids / mode / threshold / depth_points must repeat the march call's values (they fix the workspace
  * layout).  Features need stride_c == 1; no alignment requirement. */
 int cnrma_rma_fill(const cnrma_grid *grid, const float *pinv, const cnrma_features *features, int grids,
