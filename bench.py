@@ -28,8 +28,8 @@ sys.path.insert(0, ROOT)
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--config", default="cfg2")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--threshold", type=float, default=0.05)
@@ -74,7 +74,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -138,6 +138,17 @@ def cpu_features(sc, views):
     return rng.standard_normal((views, sc.channels, sc.height, sc.width), dtype=np.float32)
 
 
+def cpu_sample_views(oracle, sc, threshold, target_s, requested):
+    """How many of the scene's views one CPU pass should cover to take about `target_s` seconds (probe: 2 views)."""
+    if requested:
+        return min(requested, sc.views)
+    probe = cpu_features(sc, 2)
+    cpu_step(oracle, sc, probe, 2, threshold)               # page in, spin up the thread pool
+    a, b, _ = cpu_step(oracle, sc, probe, 2, threshold)
+    per_view = max((a + b) / 2.0, 1e-4)
+    return int(max(2, min(sc.views, target_s / per_view)))
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -148,9 +159,9 @@ def run_reference_arm(args):
     oracle.build()
     cores = oracle.num_threads()
     sc = synthetic.make_scene(args.config, seed=0, with_features=False)
-    views = args.cpu_views or min(sc.views, 8)
+    views = cpu_sample_views(oracle, sc, args.threshold, 2.0, args.cpu_views)     # ~2 s of CPU work per step
     feats = cpu_features(sc, views)
-    for _ in range(args.warmup):
+    for _ in range(min(args.warmup, 2)):
         cpu_step(oracle, sc, feats, views, args.threshold)
     t0 = time.perf_counter()
     ta = tb = 0.0
@@ -164,7 +175,7 @@ def run_reference_arm(args):
     sample = f"first {views} of {sc.views} views of the {args.config} scene per step, both stages, C oracle + OpenMP"
     line = {
         "impl": "reference", "metric": "voxel_views_per_s", "value": value, "unit": "voxel*views/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.config, sc), "sample": sample},
         "scenes_per_s": (views / sc.views) * args.steps / dt,
@@ -340,7 +351,8 @@ def main():
         "ray_steps_per_s": world * sc.ray_steps / (ms_step * 1e-3),
         "stage_ms": {"stage_a": ms_a, "march": ms_march, "fill": ms_fill},
         "kernels": kernels, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
-        "gpu_launches": (5 if args.stage == "both" else (1 if args.stage == "a" else 4)) * args.steps,
+        # aggregate_views | tsdf_sigmoid, dist_boundary, 3 x dist_pass, march_neus, scan_blocks | fill_rows_tma
+        "gpu_launches": (9 if args.stage == "both" else (1 if args.stage == "a" else 8)) * args.steps,
     }
     print(json.dumps(line))
     if world > 1:
@@ -391,8 +403,11 @@ def run_view_sharded(args, cn, dev, rank, world):
 
 
 def run_e2e(args, cn, sc, feats, proj, tsdf, dev, world, m_rows):
-    """Same step through the public host API with HOST buffers: pinned inputs copied H2D every step, results
-    (volume, count, points) copied D2H every step; timed with CUDA events, max over ranks."""
+    """Same step through the public host API with HOST buffers: every step copies its inputs from pinned host
+    memory to the device and its results (volume, count, points) back to pinned host memory.  Three streams
+    (copy-in, compute, copy-out) with double-buffered device inputs, so the next scene's upload and the previous
+    scene's download overlap with the kernels; timed with CUDA events from the first upload to the last download,
+    max over ranks."""
     import torch
     import torch.distributed as dist
     V, C, H, W = sc.views, sc.channels, sc.height, sc.width
@@ -406,32 +421,57 @@ def run_e2e(args, cn, sc, feats, proj, tsdf, dev, world, m_rows):
     h_pts = torch.empty((int(m_rows * 1.05) + 1024, 3 + C), dtype=torch.float32).pin_memory()
     ag = cn.RayMarchingAggregator(sc.voxel_size, sc.voxel_dim, origin=sc.origin.tolist(), backbone2d_stride=sc.stride,
                                   neus_threshold=args.threshold)
+    s_in, s_cmp, s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
+    slots = [dict(feats=torch.empty_like(h_feats, device=dev), proj=torch.empty_like(h_proj, device=dev),
+                  tsdf=torch.empty_like(h_tsdf, device=dev), loaded=torch.cuda.Event(), used=torch.cuda.Event())
+             for _ in range(2)]
 
-    def one():
-        d_feats = h_feats.to(dev, non_blocking=True).permute(0, 1, 4, 2, 3)
-        d_proj = h_proj.to(dev, non_blocking=True)
-        d_tsdf = h_tsdf.to(dev, non_blocking=True)
-        ag.initialize_volume()
-        for v in range(V):
-            ag.aggregate_2d_features(d_proj[v], d_feats[v])
-        ag.clear_3d_features()
-        ag.aggregate_2d_features_ray_marching(d_proj, d_feats, d_tsdf)
-        pts = ag.points_detection[0]
-        h_vol.copy_(ag.volume.permute(0, 2, 3, 4, 1), non_blocking=True)
-        h_cnt.copy_(ag._sum[1], non_blocking=True)
-        h_pts[: pts.shape[0]].copy_(pts, non_blocking=True)
+    def upload(k):
+        sl = slots[k % 2]
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(sl["used"])                      # the kernels that read this slot two steps ago are done
+            sl["feats"].copy_(h_feats, non_blocking=True)
+            sl["proj"].copy_(h_proj, non_blocking=True)
+            sl["tsdf"].copy_(h_tsdf, non_blocking=True)
+            sl["loaded"].record(s_in)
+
+    def compute_and_download(k):
+        sl = slots[k % 2]
+        with torch.cuda.stream(s_cmp):
+            s_cmp.wait_event(sl["loaded"])
+            d_feats = sl["feats"].permute(0, 1, 4, 2, 3)
+            ag.initialize_volume()
+            for v in range(V):
+                ag.aggregate_2d_features(sl["proj"][v], d_feats[v])
+            ag.clear_3d_features()
+            ag.aggregate_2d_features_ray_marching(h_proj, d_feats, sl["tsdf"])   # cameras also known on the host
+            sl["used"].record(s_cmp)
+            pts, vol, cnt = ag.points_detection[0], ag.volume, ag._sum[1]
+        with torch.cuda.stream(s_out):
+            s_out.wait_stream(s_cmp)
+            h_vol.copy_(vol.permute(0, 2, 3, 4, 1), non_blocking=True)
+            h_cnt.copy_(cnt, non_blocking=True)
+            h_pts[: pts.shape[0]].copy_(pts, non_blocking=True)
+            for t in (pts, vol, cnt):
+                t.record_stream(s_out)
         return pts.shape[0]
 
-    steps = max(2, min(args.steps, 5))
-    one()
+    steps = max(2, min(args.steps, 6))
+    upload(0)
+    compute_and_download(0)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(steps):
-        rows = one()
-    t1.record()
+    t0.record(s_in)
+    upload(0)
+    for k in range(steps):
+        if k + 1 < steps:
+            upload(k + 1)
+        rows = compute_and_download(k)
+    s_out.wait_stream(s_cmp)
+    s_out.wait_stream(s_in)
+    t1.record(s_out)
     torch.cuda.synchronize()
     ms = t0.elapsed_time(t1)
     if world > 1:
@@ -443,7 +483,9 @@ def run_e2e(args, cn, sc, feats, proj, tsdf, dev, world, m_rows):
     d2h = h_vol.numel() * 4 + h_cnt.numel() * 4 + rows * (3 + C) * 4
     return {"value": world * sc.voxel_views / (ms * 1e-3), "unit": "voxel*views/s", "ms_per_step": ms,
             "scenes_per_s": world / (ms * 1e-3), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
-            "api": "RayMarchingAggregator (host mirror of the reference detector's aggregation methods)"}
+            "pcie_gbs": (h2d + d2h) / ms / 1e6,
+            "api": "RayMarchingAggregator (host mirror of the reference detector's aggregation methods); "
+                   "copy-in / compute / copy-out on three streams"}
 
 
 def run_cpu_baseline(args, sc):
@@ -452,9 +494,8 @@ def run_cpu_baseline(args, sc):
     import oracle
     oracle.build()
     cores = oracle.num_threads()
-    views = args.cpu_views or min(sc.views, 8)
+    views = cpu_sample_views(oracle, sc, args.threshold, 12.0, args.cpu_views)    # ~10-30 s of CPU work
     feats = cpu_features(sc, views)
-    cpu_step(oracle, sc, feats, min(views, 2), args.threshold)      # warm-up (page in, thread pool)
     a, b, m = cpu_step(oracle, sc, feats, views, args.threshold)
     vv = views * sc.nvox
     return {"value": vv / (a + b), "unit": "voxel*views/s", "cores": cores, "kind": "port",
