@@ -227,6 +227,41 @@ int cnrma_rma_scatter(const cnrma_grid *grid, const float *pinv, const cnrma_fea
                        nullptr, 0, 0, wsum, wtot, stream);
 }
 
+int cnrma_aggregate_views_backward(const cnrma_grid *grid, const cnrma_features *grad_features, const float *projections,
+                                   int64_t proj_view_stride, float stride, uint32_t flags, const float *grad_volume,
+                                   int64_t vol_stride_voxel, int64_t vol_stride_channel, const int32_t *count,
+                                   void *stream) {
+    if (!grid_ok(grid) || !projections || !grad_volume || !count || !(stride > 0.0f)) return CNRMA_ERR_ARG;
+    if (flags & ~CNRMA_AGG_MEAN) return CNRMA_ERR_ARG;
+    const int fs = features_ok(grad_features, true);
+    if (fs != CNRMA_OK) return fs;
+    if (grad_features->dtype != CNRMA_F32) return CNRMA_ERR_UNSUPPORTED;
+    const int d = device_ok();
+    if (d != CNRMA_OK) return d;
+    const cudaError_t e = run_aggregate_views_backward(to_dev(*grid), *grad_features, projections, proj_view_stride, stride,
+                                                       flags, grad_volume, vol_stride_voxel, vol_stride_channel, count,
+                                                       static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
+}
+
+int cnrma_rma_fill_backward(const cnrma_grid *grid, const cnrma_features *grad_features, int grids, int mode,
+                            float threshold, int depth_points, const void *workspace, const cnrma_rma_result *result,
+                            int normalize, const float *mean, const float *grad_rows, int64_t row_stride, void *stream) {
+    if (!grid_ok(grid) || !workspace || !result || !grad_rows) return CNRMA_ERR_ARG;
+    const int fs = features_ok(grad_features, false);
+    if (fs != CNRMA_OK) return fs;
+    if (grad_features->dtype != CNRMA_F32 || grad_features->stride_c != 1) return CNRMA_ERR_LAYOUT;
+    if (row_stride < grad_features->channels + (normalize ? 3 : 4)) return CNRMA_ERR_ARG;
+    const int d = device_ok();
+    if (d != CNRMA_OK) return d;
+    const RmaWorkspace ws = rma_workspace(grad_features->views, grad_features->height, grad_features->width, grids, mode,
+                                          threshold, depth_points, rma_brick_count(to_dev(*grid)),
+                                          (int64_t)grid->nx * grid->ny * grid->nz);
+    const cudaError_t e = run_fill_backward(*grad_features, workspace, ws, normalize, mean ? mean : &result->mean,
+                                            grad_rows, row_stride, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
+}
+
 int cnrma_rma_expand(int views, int height, int width, int grids, float threshold, const void *workspace,
                      float *weights, uint8_t *keep, void *stream) {
     if (!workspace || views <= 0 || height <= 0 || width <= 0 || grids <= 0) return CNRMA_ERR_ARG;

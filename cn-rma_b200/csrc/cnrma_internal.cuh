@@ -37,4 +37,11 @@ cudaError_t run_ray_parameters(const float *pinv, int V, int H, int W, float *o,
 cudaError_t run_expand(int64_t rays, int N, const void *workspace, const RmaWorkspace &ws, float *weights,
                        uint8_t *keep, cudaStream_t stream);
 
+// cnrma_backward.cu
+cudaError_t run_aggregate_views_backward(const GridDev &g, const cnrma_features &gf, const float *proj,
+                                         int64_t proj_stride, float stride, uint32_t flags, const float *grad_volume,
+                                         int64_t vsv, int64_t vsc, const int32_t *count, cudaStream_t stream);
+cudaError_t run_fill_backward(const cnrma_features &gf, const void *workspace, const RmaWorkspace &ws, int normalize,
+                              const float *mean, const float *grad_rows, int64_t row_stride, cudaStream_t stream);
+
 }  // namespace cnrma

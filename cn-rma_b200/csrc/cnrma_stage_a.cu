@@ -50,53 +50,6 @@ constexpr int kMaxChunkBytes = 1024;     // 64 16-byte vectors: two per lane
 constexpr int kWarpBufferBytes = 6144;   // per-warp row buffer: 4 CTAs x 8 warps x 6 KB = 192 KB per SM
 constexpr int kAggCtasPerSm = 4;
 
-// ---- mbarrier / bulk-copy primitives (PTX) ---------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-// TMA bulk copy global -> this CTA's shared memory, completion (bytes) signalled on `bar`.
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-
-// n / d and n % d for 0 <= n < 2^31, 0 < d, quotient < 2^22: float estimate, exact integer fix-up (the estimate is
-// within 1 of the true quotient), ~8 instructions instead of the ~40 of a generic 32-bit division.
-__device__ __forceinline__ void fast_divmod(int n, int d, float inv_d, int &q, int &r) {
-    q = (int)((float)n * inv_d);
-    r = n - q * d;
-    if (r < 0) { r += d; --q; }
-    else if (r >= d) { r -= d; ++q; }
-}
-
-// IEEE-correct a / n for a small positive integer n, given y = RN(1/n): q = RN(a*y); r = a - n*q (exact, FMA);
-// q' = RN(q + r*y) (Markstein).  Values whose residual could leave the normal range take the generic path.
-__device__ __forceinline__ float div_by_count(float a, float n, float y) {
-    const float mag = fabsf(a);
-    if (!(mag > 1e-30f && mag < 1e30f)) return __fdiv_rn(a, n);
-    const float q = __fmul_rn(a, y);
-    const float r = __fmaf_rn(-n, q, a);
-    return __fmaf_rn(r, y, q);
-}
-
 template <int VPL, typename T>
 __global__ void __launch_bounds__(kAggThreads, kAggCtasPerSm)
 aggregate_views_kernel(const __grid_constant__ AggParams p) {

@@ -112,6 +112,91 @@ def _projections_device(projections, device):
 
 
 # ----------------------------------------------------------------------------------------------------
+# autograd: the forward kernels run without a graph; these Functions attach the backward kernels to their
+# results (the gradient flows into the feature maps only, like in the reference: rm.py:61-64, :304, :799)
+# ----------------------------------------------------------------------------------------------------
+
+def _needs_grad(views):
+    return torch.is_grad_enabled() and any(v.requires_grad for v in views)
+
+
+def _grad_buffer(state):
+    """Zeroed fp32 channels-last gradient maps [V,B,H,W,C] and their per-view [B,C,H,W] views."""
+    V, B, Cc, H, W = state["shape"]
+    buf = torch.zeros((V, B, H, W, Cc), dtype=torch.float32, device=state["device"])
+    return buf, [buf[v].permute(0, 3, 1, 2) for v in range(V)]
+
+
+def _grad_descriptor(buf, b):
+    V, B, H, W, Cc = buf.shape
+    ptrs = (C.c_void_p * V)(*[buf[v, b].data_ptr() for v in range(V)])
+    desc = _lib.Features(V, Cc, H, W, _lib.F32, 1, W * Cc, Cc, C.cast(ptrs, C.POINTER(C.c_void_p)))
+    desc._keepalive = ptrs
+    return desc
+
+
+def _linear_voxel_strides(g, nx, ny, nz):
+    """(voxel stride, channel stride) of a [C,nx,ny,nz] tensor whose voxels are linearly addressable."""
+    sc, sx, sy, sz = g.stride()
+    if sy == nz * sz and sx == ny * nz * sz:
+        return g, sz, sc
+    g = g.contiguous()
+    return g, 1, nx * ny * nz
+
+
+class _AggregateBackward(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, volume, state, *views):
+        ctx.state = state
+        return volume.view_as(volume)
+
+    @staticmethod
+    def backward(ctx, grad_volume):
+        st = ctx.state
+        lib = _lib.load()
+        nx, ny, nz = st["voxel_dim"]
+        buf, grads = _grad_buffer(st)
+        device = st["device"]
+        with torch.cuda.device(device):
+            for b in range(st["shape"][1]):
+                g, vsv, vsc = _linear_voxel_strides(grad_volume[b].float(), nx, ny, nz)
+                desc = _grad_descriptor(buf, b)
+                _lib.check(lib.cnrma_aggregate_views_backward(
+                    C.byref(st["grid"]), C.byref(desc), C.c_void_p(st["P"][0, b].data_ptr()), st["shape"][1] * 12,
+                    float(st["stride"]), _lib.AGG_MEAN if st["mean"] else 0, C.c_void_p(g.data_ptr()), vsv, vsc,
+                    C.c_void_p(st["count"][b].data_ptr()), _stream(device)), "cnrma_aggregate_views_backward")
+        return (None, None) + tuple(gv.to(dt) if need else None
+                                    for gv, dt, need in zip(grads, st["dtypes"], st["needs"]))
+
+
+class _RmaRowsBackward(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rows, state, *views):
+        ctx.state = state
+        return rows.view_as(rows)
+
+    @staticmethod
+    def backward(ctx, grad_rows):
+        st = ctx.state
+        lib = _lib.load()
+        m = st["march"]
+        buf, grads = _grad_buffer(st)
+        device = st["device"]
+        g = grad_rows.float().contiguous()
+        mean_t = st["mean"]
+        with torch.cuda.device(device):
+            desc = _grad_descriptor(buf, st["b"])
+            if g.shape[0] > 0:
+                _lib.check(lib.cnrma_rma_fill_backward(
+                    C.byref(st["grid"]), C.byref(desc), m.grids, m.mode, m.threshold, m.depth_points,
+                    C.c_void_p(m.workspace.data_ptr()), C.c_void_p(m.result.data_ptr()), 1 if st["normalize"] else 0,
+                    C.c_void_p(mean_t.data_ptr()) if mean_t is not None else None, C.c_void_p(g.data_ptr()),
+                    g.shape[1], _stream(device)), "cnrma_rma_fill_backward")
+        return (None, None) + tuple(gv.to(dt) if need else None
+                                    for gv, dt, need in zip(grads, st["dtypes"], st["needs"]))
+
+
+# ----------------------------------------------------------------------------------------------------
 # Stage A
 # ----------------------------------------------------------------------------------------------------
 
@@ -167,6 +252,10 @@ def aggregate_views(projections, features, voxel_dim, voxel_size, origin, stride
         if accumulate is None or accumulate:
             flags |= _lib.AGG_ACCUMULATE
         _check_out(volume, count, fs.B, fs.C, nx, ny, nz, count_f32)
+    view_list = _as_view_list(features)
+    with_grad = _needs_grad(view_list)
+    if with_grad and (out is not None or count_f32):
+        raise CnrmaError("autograd through aggregate_views needs the one-call form (no `out=` accumulation)")
     with torch.cuda.device(device):
         for b in range(fs.B):
             desc = fs.descriptor(b)
@@ -176,6 +265,11 @@ def aggregate_views(projections, features, voxel_dim, voxel_size, origin, stride
                                                  vb.stride(3), vb.stride(0), C.c_void_p(count[b].data_ptr()),
                                                  C.c_void_p(valid[b].data_ptr()) if valid is not None else None,
                                                  _stream(device)), "cnrma_aggregate_views")
+    if with_grad:
+        state = dict(shape=(fs.V, fs.B, fs.C, fs.H, fs.W), device=device, voxel_dim=(nx, ny, nz), grid=grid, P=P,
+                     stride=stride, mean=bool(mean), count=count, dtypes=[v.dtype for v in view_list],
+                     needs=[v.requires_grad for v in view_list])
+        volume = _AggregateBackward.apply(volume, state, *view_list)
     return volume, count, valid
 
 
@@ -394,7 +488,9 @@ def rma_points(projections, features, tsdf, voxel_dim, voxel_size, origin, strid
     returns.  A batch element with no kept sample yields an empty [0, .] tensor (the reference raises).
     `mean_hook(weight_sum, rows, device) -> float32 CUDA tensor [1]` overrides the divisor of rm.py:303."""
     _check_mode(mode, threshold, depth_points)
-    fs = _FeatureStack(_as_view_list(features), need_vector_layout=False)
+    view_list = _as_view_list(features)
+    with_grad = _needs_grad(view_list)
+    fs = _FeatureStack(view_list, need_vector_layout=False)
     device = fs.device
     if not isinstance(projections, torch.Tensor):
         projections = torch.stack(list(projections), dim=0)
@@ -409,6 +505,12 @@ def rma_points(projections, features, tsdf, voxel_dim, voxel_size, origin, strid
             key = (device.index, b, fs.V, fs.C, fs.H, fs.W, tuple(int(v) for v in voxel_dim), int(grids), mode,
                    threshold, depth_points, bool(normalize))
             rows, res = _march_and_fill(fs, b, m, grid, normalize, mean_hook, key)
+            if with_grad:
+                mean_t = mean_hook(res.weight_sum, res.rows, device) if (mean_hook and normalize) else None
+                state = dict(shape=(fs.V, fs.B, fs.C, fs.H, fs.W), device=device, grid=grid, march=m, b=b,
+                             normalize=bool(normalize), mean=mean_t, dtypes=[v.dtype for v in view_list],
+                             needs=[v.requires_grad for v in view_list])
+                rows = _RmaRowsBackward.apply(rows, state, *view_list)
             out.append(rows)
             stats.append(dict(rows=int(res.rows), weight_sum=float(res.weight_sum), mean=float(res.mean)))
     return (out, stats) if return_stats else out

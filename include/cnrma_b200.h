@@ -177,6 +177,28 @@ int cnrma_rma_scatter(const cnrma_grid *grid, const float *pinv, const cnrma_fea
                       float t_one, int mode, float threshold, int depth_points, const void *workspace, float *wsum,
                       float *wtot, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Backward of the two feature gathers (what autograd does for rm.py:61-64 / :243 / :251 and rm.py:799 / :304 when
+ * the detector trains, rm.py:409-451).  Gradients are fp32, channels-last, described like feature maps.
+ * ------------------------------------------------------------------------------------------- */
+
+/* d features of cnrma_aggregate_views: grad_features[view][py][px][:] += grad_volume[voxel][:] (/ count[voxel]
+ * with CNRMA_AGG_MEAN) for every view that sees the voxel.  grad_features must be zeroed by the caller (the adds are
+ * fp32 reductions performed by the memory system; order-dependent rounding like index_put_(accumulate=True)).
+ * `count` is the forward's int32 view count. */
+int cnrma_aggregate_views_backward(const cnrma_grid *grid, const cnrma_features *grad_features, const float *projections,
+                                   int64_t proj_view_stride, float stride, uint32_t flags, const float *grad_volume,
+                                   int64_t vol_stride_voxel, int64_t vol_stride_channel, const int32_t *count,
+                                   void *stream);
+
+/* d features of cnrma_rma_fill: grad_features[view][v][u][:] = sum over the rows of that ray of
+ * grad_rows[row][3 + :] * w/mean (normalize) or grad_rows[row][4 + :] (un-normalised rows).  Weights and positions
+ * carry no gradient (rm.py:705).  Every pixel row is written (zeros where the ray kept nothing); needs the
+ * workspace / result of the forward march. */
+int cnrma_rma_fill_backward(const cnrma_grid *grid, const cnrma_features *grad_features, int grids, int mode,
+                            float threshold, int depth_points, const void *workspace, const cnrma_rma_result *result,
+                            int normalize, const float *mean, const float *grad_rows, int64_t row_stride, void *stream);
+
 /* Dense per-sample view of the march records for parity tests: weights f32 [V*H*W*N] (0 where not kept,
  * i.e. rm.py:767 `weights * valid_final`) and keep uint8 [V*H*W*N].  NEUS mode only. */
 int cnrma_rma_expand(int views, int height, int width, int grids, float threshold, const void *workspace,

@@ -12,7 +12,8 @@ Each fixture stores the inputs and what the reference's own code returns for the
   Stage B  rm.py:687-807 ray_projection_neus per view -> rows [M_v, 4+C] (or "None" marker);
            rm.py:260-307 aggregate_2d_features_ray_marching -> points [M, 3+C];
            rm.py:809-956 ray_projection_depth for depth_points 0..2 through the same aggregate call.
-           Also the intermediates rm.py:71-111 (o, d) and the dense weights of view 0.
+           Also the intermediates rm.py:71-111 (o, d) of view 0.
+  Grads    d(sum(volume * G)) / d features and d(sum(points * G')) / d features from the reference's own autograd.
 
 The fixtures are the pin for oracle/cnrma_oracle.c (tests/test_oracle_golden.py) and a second
 check for the CUDA path (tests/test_gpu_golden.py).
@@ -158,6 +159,36 @@ def run_case(name, sc, opt):
         w = rows[:, 3:4] / torch.mean(rows[:, 3:4])
         out[f"depth{k}_rows"] = rows.numpy()
         out[f"depth{k}_points"] = torch.concat((rows[:, 0:3], rows[:, 4:] * w), dim=1).numpy()
+
+    # ---- gradients w.r.t. the feature maps (what autograd gives the reference in forward_train, rm.py:409-451)
+    gen = torch.Generator().manual_seed(1234)
+    fg = torch.from_numpy(sc.features).unsqueeze(1).clone().requires_grad_(True)
+    sg = ref_shim.make_self(sc.voxel_dim, sc.voxel_size, origin, stride=stride, neus_threshold=thr)
+    for v in range(V):
+        sg.aggregate_2d_features(projs[v], fg[v])
+    sg.clear_3d_features()
+    g_vol = torch.randn(sg.volume.shape, generator=gen)
+    (sg.volume * g_vol).sum().backward()
+    out["grad_volume"] = g_vol[0].numpy()
+    out["grad_features_stage_a"] = fg.grad[:, 0].numpy().copy()
+    fg.grad = None
+    chunks = []
+    for v in range(V):
+        p = projs[v].clone()
+        p[:, :2, :] = p[:, :2, :] / stride
+        try:
+            r = sg.ray_projection_neus(p, fg[v], tsdf, grids=sc.grids, weight_threshold=thr)
+        except Exception:
+            r = None
+        if r is not None:
+            chunks.append(r[0])
+    rows_g = torch.concat(chunks, dim=0)
+    w_g = rows_g[:, 3:4] / torch.mean(rows_g[:, 3:4])                       # rm.py:298-307
+    pts_g = torch.concat((rows_g[:, 0:3], rows_g[:, 4:] * w_g), dim=1)
+    g_pts = torch.randn(pts_g.shape, generator=gen)
+    (pts_g * g_pts).sum().backward()
+    out["grad_points"] = g_pts.numpy()
+    out["grad_features_stage_b"] = fg.grad[:, 0].numpy().copy()
 
     path = os.path.join(ROOT, "tests", "golden", name + ".npz")
     np.savez_compressed(path, **out)
