@@ -120,6 +120,22 @@ def _needs_grad(views):
     return torch.is_grad_enabled() and any(v.requires_grad for v in views)
 
 
+def _autograd_inputs(features, view_list):
+    """What the backward Functions differentiate with respect to: the stacked [V,B,C,H,W] tensor itself when the
+    caller passed one (a single gradient tensor comes back, instead of V select-backward nodes that each
+    materialise a full-size zero tensor), else the per-view tensors."""
+    if isinstance(features, torch.Tensor):
+        return [features], True
+    return view_list, False
+
+
+def _grads_out(st, buf, grads):
+    if st["stacked"]:
+        g = buf.permute(0, 1, 4, 2, 3)
+        return (None, None, g.to(st["dtypes"][0]) if st["needs"][0] else None)
+    return (None, None) + tuple(gv.to(dt) if need else None for gv, dt, need in zip(grads, st["dtypes"], st["needs"]))
+
+
 def _grad_buffer(state):
     """Zeroed fp32 channels-last gradient maps [V,B,H,W,C] and their per-view [B,C,H,W] views."""
     V, B, Cc, H, W = state["shape"]
@@ -165,8 +181,7 @@ class _AggregateBackward(torch.autograd.Function):
                     C.byref(st["grid"]), C.byref(desc), C.c_void_p(st["P"][0, b].data_ptr()), st["shape"][1] * 12,
                     float(st["stride"]), _lib.AGG_MEAN if st["mean"] else 0, C.c_void_p(g.data_ptr()), vsv, vsc,
                     C.c_void_p(st["count"][b].data_ptr()), _stream(device)), "cnrma_aggregate_views_backward")
-        return (None, None) + tuple(gv.to(dt) if need else None
-                                    for gv, dt, need in zip(grads, st["dtypes"], st["needs"]))
+        return _grads_out(st, buf, grads)
 
 
 class _RmaRowsBackward(torch.autograd.Function):
@@ -192,8 +207,7 @@ class _RmaRowsBackward(torch.autograd.Function):
                     C.c_void_p(m.workspace.data_ptr()), C.c_void_p(m.result.data_ptr()), 1 if st["normalize"] else 0,
                     C.c_void_p(mean_t.data_ptr()) if mean_t is not None else None, C.c_void_p(g.data_ptr()),
                     g.shape[1], _stream(device)), "cnrma_rma_fill_backward")
-        return (None, None) + tuple(gv.to(dt) if need else None
-                                    for gv, dt, need in zip(grads, st["dtypes"], st["needs"]))
+        return _grads_out(st, buf, grads)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -266,10 +280,11 @@ def aggregate_views(projections, features, voxel_dim, voxel_size, origin, stride
                                                  C.c_void_p(valid[b].data_ptr()) if valid is not None else None,
                                                  _stream(device)), "cnrma_aggregate_views")
     if with_grad:
+        inputs, stacked = _autograd_inputs(features, view_list)
         state = dict(shape=(fs.V, fs.B, fs.C, fs.H, fs.W), device=device, voxel_dim=(nx, ny, nz), grid=grid, P=P,
-                     stride=stride, mean=bool(mean), count=count, dtypes=[v.dtype for v in view_list],
-                     needs=[v.requires_grad for v in view_list])
-        volume = _AggregateBackward.apply(volume, state, *view_list)
+                     stride=stride, mean=bool(mean), count=count, stacked=stacked, dtypes=[v.dtype for v in inputs],
+                     needs=[v.requires_grad for v in inputs])
+        volume = _AggregateBackward.apply(volume, state, *inputs)
     return volume, count, valid
 
 
@@ -507,10 +522,11 @@ def rma_points(projections, features, tsdf, voxel_dim, voxel_size, origin, strid
             rows, res = _march_and_fill(fs, b, m, grid, normalize, mean_hook, key)
             if with_grad:
                 mean_t = mean_hook(res.weight_sum, res.rows, device) if (mean_hook and normalize) else None
+                inputs, stacked = _autograd_inputs(features, view_list)
                 state = dict(shape=(fs.V, fs.B, fs.C, fs.H, fs.W), device=device, grid=grid, march=m, b=b,
-                             normalize=bool(normalize), mean=mean_t, dtypes=[v.dtype for v in view_list],
-                             needs=[v.requires_grad for v in view_list])
-                rows = _RmaRowsBackward.apply(rows, state, *view_list)
+                             normalize=bool(normalize), mean=mean_t, stacked=stacked,
+                             dtypes=[v.dtype for v in inputs], needs=[v.requires_grad for v in inputs])
+                rows = _RmaRowsBackward.apply(rows, state, *inputs)
             out.append(rows)
             stats.append(dict(rows=int(res.rows), weight_sum=float(res.weight_sum), mean=float(res.mean)))
     return (out, stats) if return_stats else out
