@@ -190,7 +190,7 @@ int cnrma_rma_march(const cnrma_grid *grid, const float *pinv, int views, int he
 static int fill_common(const cnrma_grid *grid, const float *pinv, const cnrma_features *features, int grids,
                        float t_one, int mode, float threshold, int depth_points, const void *workspace, int normalize,
                        const float *mean, float *rows, int64_t row_stride, int64_t capacity, float *wsum, float *wtot,
-                       void *stream) {
+                       const uint8_t *sel_mask, const int32_t *sel_prefix, const float *sel_off_host, void *stream) {
     if (!grid_ok(grid) || !pinv || !workspace) return CNRMA_ERR_ARG;
     const int fs = features_ok(features, false);
     if (fs != CNRMA_OK) return fs;
@@ -200,7 +200,8 @@ static int fill_common(const cnrma_grid *grid, const float *pinv, const cnrma_fe
     const RmaWorkspace ws = rma_workspace(features->views, features->height, features->width, grids, mode, threshold,
                                           depth_points);
     const cudaError_t e = run_fill(to_dev(*grid), pinv, *features, t_one, mode, workspace, ws, normalize, mean, rows,
-                                   row_stride, capacity, wsum, wtot, static_cast<cudaStream_t>(stream));
+                                   row_stride, capacity, wsum, wtot, sel_mask, sel_prefix, sel_off_host,
+                                   static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
 }
 
@@ -216,7 +217,51 @@ int cnrma_rma_fill(const cnrma_grid *grid, const float *pinv, const cnrma_featur
     if (rows_host == 0 || capacity == 0) return CNRMA_OK;
     const float *mean_ptr = mean ? mean : &result->mean;
     return fill_common(grid, pinv, features, grids, t_one, mode, threshold, depth_points, workspace, normalize,
-                       mean_ptr, rows, row_stride, capacity, nullptr, nullptr, stream);
+                       mean_ptr, rows, row_stride, capacity, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+int cnrma_rma_fill_selected(const cnrma_grid *grid, const float *pinv, const cnrma_features *features, int grids,
+                            float t_one, int mode, float threshold, int depth_points, const void *workspace,
+                            const cnrma_rma_result *result, int normalize, const float *mean, const uint8_t *mask,
+                            const int32_t *prefix, const float *offset_host, float *rows, int64_t row_stride,
+                            int64_t capacity, void *stream) {
+    if (!rows || !result || !mask || !prefix || !offset_host || capacity < 0 || !features) return CNRMA_ERR_ARG;
+    const int cols = features->channels + (normalize ? 3 : 4);
+    if (row_stride < cols) return CNRMA_ERR_ARG;
+    if (capacity == 0) return CNRMA_OK;
+    const float *mean_ptr = mean ? mean : &result->mean;
+    return fill_common(grid, pinv, features, grids, t_one, mode, threshold, depth_points, workspace, normalize,
+                       mean_ptr, rows, row_stride, capacity, nullptr, nullptr, mask, prefix, offset_host, stream);
+}
+
+int cnrma_handoff_workspace_bytes(int64_t rows, size_t *bytes) {
+    if (!bytes || rows < 0) return CNRMA_ERR_ARG;
+    *bytes = handoff_workspace_bytes(rows);
+    return CNRMA_OK;
+}
+
+int cnrma_mask_prefix(const uint8_t *mask, int64_t rows, void *workspace, size_t workspace_bytes, int32_t *prefix,
+                      int64_t *kept, void *stream) {
+    if (!mask || !workspace || !prefix || !kept || rows < 0) return CNRMA_ERR_ARG;
+    if (rows >= ((int64_t)1 << 31)) return CNRMA_ERR_UNSUPPORTED;
+    if (workspace_bytes < handoff_workspace_bytes(rows)) return CNRMA_ERR_CAPACITY;
+    const int d = device_ok();
+    if (d != CNRMA_OK) return d;
+    const cudaError_t e = run_mask_prefix(mask, rows, workspace, prefix, kept, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
+}
+
+int cnrma_select_rows(const float *rows, int64_t row_stride, int cols, int64_t n_rows, const uint8_t *mask,
+                      const int32_t *prefix, const float *offset_host, float *out, int64_t out_stride,
+                      int64_t capacity, void *stream) {
+    if (!rows || !mask || !prefix || !offset_host || !out || cols < 3 || row_stride < cols || out_stride < cols ||
+        n_rows < 0 || capacity < 0)
+        return CNRMA_ERR_ARG;
+    const int d = device_ok();
+    if (d != CNRMA_OK) return d;
+    const cudaError_t e = run_select_rows(rows, row_stride, cols, n_rows, mask, prefix, offset_host, out, out_stride,
+                                          capacity, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
 }
 
 int cnrma_rma_scatter(const cnrma_grid *grid, const float *pinv, const cnrma_features *features, int grids,
@@ -224,7 +269,7 @@ int cnrma_rma_scatter(const cnrma_grid *grid, const float *pinv, const cnrma_fea
                       float *wtot, void *stream) {
     if (!wsum || !wtot) return CNRMA_ERR_ARG;
     return fill_common(grid, pinv, features, grids, t_one, mode, threshold, depth_points, workspace, 0, nullptr,
-                       nullptr, 0, 0, wsum, wtot, stream);
+                       nullptr, 0, 0, wsum, wtot, nullptr, nullptr, nullptr, stream);
 }
 
 int cnrma_aggregate_views_backward(const cnrma_grid *grid, const cnrma_features *grad_features, const float *projections,

@@ -1,0 +1,137 @@
+// Point-cloud hand-off: what RayMarching.switch_pointcloud does between the RMA lift
+// and the sparse detector (rm.py:339-407) -- `coord + offset`, then the random sub-sampling mask of sample_points
+// (fcaf3d_transforms.py:283-296, max_points = 500000) applied with one torch.masked_select PER COLUMN (C + 3 of
+// them, rm.py:380-402).  Here: one ordered compaction of whole rows.
+//
+//   mask_prefix    exclusive prefix sum of the keep mask over the M rows (block sums -> scan -> per-row prefix)
+//   select_rows    kept rows copied in order to out[prefix[row]], the offset added to x, y, z (one rounding, like
+//                  the reference's `coord + offsets[b]`)
+// The same prefix array lets cnrma_rma_fill write ONLY the kept rows (fill_rows_kernel, `sel_*` parameters), which
+// removes ~90 % of the point-row traffic when max_points << M.
+#include "cnrma_internal.cuh"
+
+namespace cnrma {
+
+constexpr int kSelThreads = 256;
+
+__global__ void __launch_bounds__(kSelThreads) mask_block_sums_kernel(const uint8_t *__restrict__ mask, int64_t M,
+                                                                      int32_t *__restrict__ blk) {
+    __shared__ int s[kSelThreads / kWarp];
+    const int64_t i = (int64_t)blockIdx.x * kSelThreads + threadIdx.x;
+    int v = (i < M && mask[i]) ? 1 : 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) s[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int k = 0; k < kSelThreads / kWarp; ++k) t += s[k];
+        blk[blockIdx.x] = t;
+    }
+}
+
+// one CTA: exclusive scan of the block sums (int64 offsets) and the total
+__global__ void __launch_bounds__(1024) scan_i32_kernel(const int32_t *__restrict__ blk, int64_t *__restrict__ blk_off,
+                                                        int64_t n, int64_t *__restrict__ total) {
+    __shared__ int64_t s[1024];
+    const int t = threadIdx.x;
+    const int64_t per = (n + 1023) / 1024;
+    const int64_t lo = (int64_t)t * per, hi = (lo + per < n) ? lo + per : n;
+    int64_t sum = 0;
+    for (int64_t i = lo; i < hi; ++i) sum += blk[i];
+    s[t] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int64_t add = (t >= o) ? s[t - o] : 0;
+        __syncthreads();
+        s[t] += add;
+        __syncthreads();
+    }
+    int64_t run = s[t] - sum;
+    for (int64_t i = lo; i < hi; ++i) {
+        blk_off[i] = run;
+        run += blk[i];
+    }
+    if (t == 1023) *total = s[t];
+}
+
+__global__ void __launch_bounds__(kSelThreads) mask_prefix_kernel(const uint8_t *__restrict__ mask, int64_t M,
+                                                                  const int64_t *__restrict__ blk_off,
+                                                                  int32_t *__restrict__ prefix) {
+    __shared__ int s[kSelThreads / kWarp];
+    const int64_t i = (int64_t)blockIdx.x * kSelThreads + threadIdx.x;
+    const int v = (i < M && mask[i]) ? 1 : 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int nn = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += nn;
+    }
+    if (lane == 31) s[warp] = incl;
+    __syncthreads();
+    int64_t base = blk_off[blockIdx.x];
+    for (int k = 0; k < warp; ++k) base += s[k];
+    if (i < M) prefix[i] = (int32_t)(base + incl - v);
+}
+
+// one warp per 32 rows; kept rows are copied whole, coalesced
+__global__ void __launch_bounds__(kSelThreads) select_rows_kernel(const float *__restrict__ rows, int64_t row_stride,
+                                                                  int cols, int64_t M, const uint8_t *__restrict__ mask,
+                                                                  const int32_t *__restrict__ prefix, float ox, float oy,
+                                                                  float oz, float *__restrict__ out, int64_t out_stride,
+                                                                  int64_t capacity) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (kSelThreads / kWarp) + (threadIdx.x >> 5);
+    const int64_t r0 = warp * 32;
+    if (r0 >= M) return;
+    const int64_t mine = r0 + lane;
+    const bool keep = mine < M && mask[mine];
+    const int dst_mine = keep ? prefix[mine] : -1;
+    const unsigned bits = __ballot_sync(0xffffffffu, keep);
+    for (unsigned b = bits; b; b &= b - 1) {
+        const int k = __ffs(b) - 1;
+        const int64_t dst = __shfl_sync(0xffffffffu, dst_mine, k);
+        if (dst >= capacity) continue;
+        const float *src = rows + (r0 + k) * row_stride;
+        float *d = out + dst * out_stride;
+        for (int c = lane; c < cols; c += 32) {
+            float v = __ldg(src + c);
+            if (c < 3) v = __fadd_rn(v, c == 0 ? ox : (c == 1 ? oy : oz));   // coord + offset (rm.py:365)
+            __stcs(d + c, v);
+        }
+    }
+}
+
+size_t handoff_workspace_bytes(int64_t M) {
+    const int64_t blocks = (M + kSelThreads - 1) / kSelThreads;
+    return ((size_t)blocks * 4 + 255) / 256 * 256 + ((size_t)blocks * 8 + 255) / 256 * 256 + 256;
+}
+
+// prefix[row] for all rows and *total (device int64) = number of kept rows
+cudaError_t run_mask_prefix(const uint8_t *mask, int64_t M, void *workspace, int32_t *prefix, int64_t *total,
+                            cudaStream_t stream) {
+    const int64_t blocks = (M + kSelThreads - 1) / kSelThreads;
+    unsigned char *base = static_cast<unsigned char *>(workspace);
+    int32_t *blk = reinterpret_cast<int32_t *>(base);
+    int64_t *blk_off = reinterpret_cast<int64_t *>(base + ((size_t)blocks * 4 + 255) / 256 * 256);
+    if (M == 0) return cudaMemsetAsync(total, 0, sizeof(int64_t), stream);
+    mask_block_sums_kernel<<<(unsigned)blocks, kSelThreads, 0, stream>>>(mask, M, blk);
+    scan_i32_kernel<<<1, 1024, 0, stream>>>(blk, blk_off, blocks, total);
+    mask_prefix_kernel<<<(unsigned)blocks, kSelThreads, 0, stream>>>(mask, M, blk_off, prefix);
+    return cudaGetLastError();
+}
+
+cudaError_t run_select_rows(const float *rows, int64_t row_stride, int cols, int64_t M, const uint8_t *mask,
+                            const int32_t *prefix, const float *offset3_host, float *out, int64_t out_stride,
+                            int64_t capacity, cudaStream_t stream) {
+    if (M == 0) return cudaSuccess;
+    const int64_t warps = (M + 31) / 32;
+    const unsigned blocks = (unsigned)((warps + (kSelThreads / kWarp) - 1) / (kSelThreads / kWarp));
+    select_rows_kernel<<<blocks, kSelThreads, 0, stream>>>(rows, row_stride, cols, M, mask, prefix, offset3_host[0],
+                                                          offset3_host[1], offset3_host[2], out, out_stride, capacity);
+    return cudaGetLastError();
+}
+
+}  // namespace cnrma

@@ -32,10 +32,19 @@ cudaError_t run_march(const GridDev &g, const float *pinv, int V, int H, int W, 
                       cnrma_rma_result *result, cudaStream_t stream);
 cudaError_t run_fill(const GridDev &g, const float *pinv, const cnrma_features &f, float t_one, int mode,
                      const void *workspace, const RmaWorkspace &ws, int normalize, const float *mean, float *rows,
-                     int64_t row_stride, int64_t capacity, float *wsum, float *wtot, cudaStream_t stream);
+                     int64_t row_stride, int64_t capacity, float *wsum, float *wtot, const uint8_t *sel_mask,
+                     const int32_t *sel_prefix, const float *sel_off_host, cudaStream_t stream);
 cudaError_t run_ray_parameters(const float *pinv, int V, int H, int W, float *o, float *d, cudaStream_t stream);
 cudaError_t run_expand(int64_t rays, int N, const void *workspace, const RmaWorkspace &ws, float *weights,
                        uint8_t *keep, cudaStream_t stream);
+
+// cnrma_handoff.cu
+size_t handoff_workspace_bytes(int64_t M);
+cudaError_t run_mask_prefix(const uint8_t *mask, int64_t M, void *workspace, int32_t *prefix, int64_t *total,
+                            cudaStream_t stream);
+cudaError_t run_select_rows(const float *rows, int64_t row_stride, int cols, int64_t M, const uint8_t *mask,
+                            const int32_t *prefix, const float *offset3_host, float *out, int64_t out_stride,
+                            int64_t capacity, cudaStream_t stream);
 
 // cnrma_backward.cu
 cudaError_t run_aggregate_views_backward(const GridDev &g, const cnrma_features &gf, const float *proj,

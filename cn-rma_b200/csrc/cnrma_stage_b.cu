@@ -414,6 +414,9 @@ struct FillParams {
     float *rows;
     int64_t row_stride;
     int64_t capacity;     // rows the output buffer holds: rows beyond it are dropped (speculative launches)
+    const uint8_t *sel_mask;     // optional hand-off selection: only rows with sel_mask[row] != 0 are written,
+    const int32_t *sel_prefix;   // at row index sel_prefix[row], with sel_off added to x, y, z (rm.py:365, :380-402)
+    float sel_off[3];
     float *wsum, *wtot;   // scatter variant
     const void *views[kMaxViewsPerLaunch];
     int view_base;        // first view of this launch
@@ -486,35 +489,50 @@ __global__ void __launch_bounds__(kRayThreads) fill_rows_kernel(const __grid_con
             const int nk = min(32, cnt - k0);
             float wk = 0.0f;       // weight that multiplies the features of this lane's record
             int64_t vox = -1;      // scatter target
-            if (lane < nk && (SCATTER || off + k0 + lane < p.capacity)) {
-                const float w = __ldg(p.rec_w + (int64_t)(k0 + lane) * p.rays + ray);
-                const float fi = __ldg(p.rec_i + (int64_t)(k0 + lane) * p.rays + ray);
-                float pos[3];
-                record_position(p, o, d, fi, pos);
+            int64_t dst_row = -1;  // output row of this lane's record (-1: not written)
+            if (lane < nk) {
+                const int64_t row_id = off + k0 + lane;
                 if (!SCATTER) {
-                    float *row = p.rows + (off + k0 + lane) * p.row_stride;
-                    row[0] = pos[0];
-                    row[1] = pos[1];
-                    row[2] = pos[2];
-                    if (p.normalize) {
-                        wk = __fdiv_rn(w, mean);   // weights / mean(weights), rm.py:303
+                    dst_row = row_id;
+                    if (p.sel_mask != nullptr) dst_row = __ldg(p.sel_mask + row_id) ? (int64_t)__ldg(p.sel_prefix + row_id) : -1;
+                    if (dst_row >= p.capacity) dst_row = -1;
+                }
+                if (SCATTER || dst_row >= 0) {
+                    const float w = __ldg(p.rec_w + (int64_t)(k0 + lane) * p.rays + ray);
+                    const float fi = __ldg(p.rec_i + (int64_t)(k0 + lane) * p.rays + ray);
+                    float pos[3];
+                    record_position(p, o, d, fi, pos);
+                    if (!SCATTER) {
+                        float *row = p.rows + dst_row * p.row_stride;
+                        if (p.sel_mask != nullptr) {   // coord + offsets[b]: one more rounding (rm.py:365)
+                            pos[0] = __fadd_rn(pos[0], p.sel_off[0]);
+                            pos[1] = __fadd_rn(pos[1], p.sel_off[1]);
+                            pos[2] = __fadd_rn(pos[2], p.sel_off[2]);
+                        }
+                        row[0] = pos[0];
+                        row[1] = pos[1];
+                        row[2] = pos[2];
+                        if (p.normalize) {
+                            wk = __fdiv_rn(w, mean);   // weights / mean(weights), rm.py:303
+                        } else {
+                            row[3] = w;
+                            wk = 1.0f;
+                        }
                     } else {
-                        row[3] = w;
-                        wk = 1.0f;
+                        const float qx = rintf(__fdiv_rn(__fsub_rn(pos[0], p.g.ox), p.g.vs));
+                        const float qy = rintf(__fdiv_rn(__fsub_rn(pos[1], p.g.oy), p.g.vs));
+                        const float qz = rintf(__fdiv_rn(__fsub_rn(pos[2], p.g.oz), p.g.vs));
+                        const bool inb = (qx >= 0.0f) && (qx < (float)p.g.nx) && (qy >= 0.0f) && (qy < (float)p.g.ny) &&
+                                         (qz >= 0.0f) && (qz < (float)p.g.nz);
+                        if (inb) {
+                            vox = ((int64_t)(int)qx * p.g.ny + (int)qy) * p.g.nz + (int)qz;
+                            atomicAdd(p.wtot + vox, w);
+                        }
+                        wk = w;
                     }
-                } else {
-                    const float qx = rintf(__fdiv_rn(__fsub_rn(pos[0], p.g.ox), p.g.vs));
-                    const float qy = rintf(__fdiv_rn(__fsub_rn(pos[1], p.g.oy), p.g.vs));
-                    const float qz = rintf(__fdiv_rn(__fsub_rn(pos[2], p.g.oz), p.g.vs));
-                    const bool inb = (qx >= 0.0f) && (qx < (float)p.g.nx) && (qy >= 0.0f) && (qy < (float)p.g.ny) &&
-                                     (qz >= 0.0f) && (qz < (float)p.g.nz);
-                    if (inb) {
-                        vox = ((int64_t)(int)qx * p.g.ny + (int)qy) * p.g.nz + (int)qz;
-                        atomicAdd(p.wtot + vox, w);
-                    }
-                    wk = w;
                 }
             }
+            if (!SCATTER && !__any_sync(0xffffffffu, dst_row >= 0)) continue;   // nothing of this ray is kept
             for (int cbase = 0; cbase < p.C; cbase += 32 * kFillRegs) {
                 float f[kFillRegs];
 #pragma unroll
@@ -525,8 +543,9 @@ __global__ void __launch_bounds__(kRayThreads) fill_rows_kernel(const __grid_con
                 for (int k = 0; k < nk; ++k) {
                     const float wn = __shfl_sync(0xffffffffu, wk, k);
                     if (!SCATTER) {
-                        if (off + k0 + k >= p.capacity) break;
-                        float *dst = p.rows + (off + k0 + k) * p.row_stride + col0;
+                        const int64_t drow = __shfl_sync(0xffffffffu, dst_row, k);
+                        if (drow < 0) continue;
+                        float *dst = p.rows + drow * p.row_stride + col0;
 #pragma unroll
                         for (int j = 0; j < kFillRegs; ++j) {
                             const int c = cbase + j * 32 + lane;
@@ -772,7 +791,8 @@ static cudaError_t launch_fill(FillParams &p, int dtype, const void *const *view
         const unsigned blocks = (unsigned)((rays + kRayThreads - 1) / kRayThreads);
         // packed rows (row_stride == columns) of up to 256 channels take the TMA-store kernel
         const int cols = p.C + (p.normalize ? 3 : 4);
-        const bool tma = !SCATTER && p.row_stride == cols && p.C <= 32 * kFillRegs && cols * 4 <= kStageBytes - 16 &&
+        const bool tma = !SCATTER && p.sel_mask == nullptr && p.row_stride == cols && p.C <= 32 * kFillRegs &&
+                         cols * 4 <= kStageBytes - 16 &&
                          reinterpret_cast<uintptr_t>(p.rows) % 4 == 0;
         if (tma) {
             const size_t smem = (size_t)(kRayThreads / kWarp) * kStageBytes;
@@ -805,7 +825,8 @@ static cudaError_t launch_fill(FillParams &p, int dtype, const void *const *view
 
 cudaError_t run_fill(const GridDev &g, const float *pinv, const cnrma_features &f, float t_one, int mode,
                      const void *workspace, const RmaWorkspace &ws, int normalize, const float *mean, float *rows,
-                     int64_t row_stride, int64_t capacity, float *wsum, float *wtot, cudaStream_t stream) {
+                     int64_t row_stride, int64_t capacity, float *wsum, float *wtot, const uint8_t *sel_mask,
+                     const int32_t *sel_prefix, const float *sel_off_host, cudaStream_t stream) {
     const unsigned char *base = static_cast<const unsigned char *>(workspace);
     FillParams p;
     p.g = g;
@@ -824,6 +845,9 @@ cudaError_t run_fill(const GridDev &g, const float *pinv, const cnrma_features &
     p.rows = rows;
     p.row_stride = row_stride;
     p.capacity = capacity;
+    p.sel_mask = sel_mask;
+    p.sel_prefix = sel_prefix;
+    for (int a = 0; a < 3; ++a) p.sel_off[a] = sel_off_host ? sel_off_host[a] : 0.0f;
     p.wsum = wsum;
     p.wtot = wtot;
     p.view_base = 0;

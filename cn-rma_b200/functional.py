@@ -603,3 +603,129 @@ def dense_rma(projections, features, tsdf, voxel_dim, voxel_size, origin, stride
                                              C.c_void_p(m.workspace.data_ptr()), C.c_void_p(wsum[b].data_ptr()),
                                              C.c_void_p(wtot[b].data_ptr()), _stream(device)), "cnrma_rma_scatter")
     return wsum, wtot
+
+
+# ----------------------------------------------------------------------------------------------------
+# Point-cloud hand-off (rm.py:339-407)
+# ----------------------------------------------------------------------------------------------------
+
+def sample_points(n, max_points, rng=None):
+    """The sub-sampling mask of datasets/pipelines/fcaf3d_transforms.py:283-296, restated call for call so that the
+    same numpy RNG state gives the same mask: a bool array [n] with max_points ones when n > max_points, all ones
+    otherwise.  Host-side by design -- the reference draws it with numpy, and only the same mask gives the same rows."""
+    import numpy as np
+    rng = np.random if rng is None else rng
+    mask = np.ones(n, dtype=bool)
+    indice = np.nonzero(mask)[0]
+    if n > max_points:
+        choices = rng.choice(n, max_points, replace=False)
+        indice = indice[choices]
+    new_mask = np.zeros_like(mask)
+    new_mask[indice] = 1
+    return new_mask
+
+
+def _mask_prefix(mask_dev):
+    lib = _lib.load()
+    device = mask_dev.device
+    n = mask_dev.numel()
+    nbytes = C.c_size_t(0)
+    _lib.check(lib.cnrma_handoff_workspace_bytes(n, C.byref(nbytes)), "cnrma_handoff_workspace_bytes")
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
+    prefix = torch.empty(n, dtype=torch.int32, device=device)
+    kept = torch.empty(1, dtype=torch.int64, device=device)
+    _lib.check(lib.cnrma_mask_prefix(C.c_void_p(mask_dev.data_ptr()), n, C.c_void_p(ws.data_ptr()), nbytes.value,
+                                     C.c_void_p(prefix.data_ptr()), C.c_void_p(kept.data_ptr()), _stream(device)),
+               "cnrma_mask_prefix")
+    return prefix, kept
+
+
+def _to_mask_dev(mask, n, device):
+    if isinstance(mask, torch.Tensor):
+        m = mask.to(device=device, dtype=torch.bool)
+    else:
+        m = torch.from_numpy(mask.astype(bool)).to(device)
+    if m.numel() != n:
+        raise ValueError("mask length must equal the number of points")
+    return m.contiguous()
+
+
+def switch_pointcloud(points, offsets, max_points=None, masks=None, rng=None):
+    """The tensor part of RayMarching.switch_pointcloud (rm.py:339-407; augmentation and boxes stay with the caller):
+    per batch element `coord + offset`, then the rows kept by sample_points' mask, in order.
+
+    points: list of [N,3+C] CUDA tensors; offsets: list of 3-vectors; masks: optional list of bool masks (else drawn
+    like the reference when max_points is set).  Returns (coords list of [Nsel,3], features list of [Nsel,C])."""
+    lib = _lib.load()
+    coords, feats = [], []
+    for b, pts in enumerate(points):
+        if not pts.is_cuda or pts.dtype != torch.float32:
+            raise CnrmaError("points must be float32 CUDA tensors")
+        device = pts.device
+        n, cols = pts.shape
+        off = _origin3(offsets[b])
+        mask = masks[b] if masks is not None else (sample_points(n, max_points, rng) if max_points is not None else None)
+        if mask is None:
+            mask_dev = torch.ones(n, dtype=torch.bool, device=device)
+            n_sel = n
+        else:
+            n_sel = int(mask.sum())
+            mask_dev = _to_mask_dev(mask, n, device)
+        out = torch.empty((n_sel, cols), dtype=torch.float32, device=device)
+        if n_sel > 0:
+            with torch.cuda.device(device):
+                prefix, _kept = _mask_prefix(mask_dev)
+                off3 = (C.c_float * 3)(*off)
+                src = pts if pts.stride(1) == 1 else pts.contiguous()
+                _lib.check(lib.cnrma_select_rows(C.c_void_p(src.data_ptr()), src.stride(0), cols, n,
+                                                 C.c_void_p(mask_dev.data_ptr()), C.c_void_p(prefix.data_ptr()), off3,
+                                                 C.c_void_p(out.data_ptr()), cols, n_sel, _stream(device)),
+                           "cnrma_select_rows")
+        coords.append(out[:, 0:3])
+        feats.append(out[:, 3:])
+    return coords, feats
+
+
+def rma_points_selected(projections, features, tsdf, voxel_dim, voxel_size, origin, stride, offsets, max_points=None,
+                        masks=None, rng=None, grids=300, mode="neus", threshold=None, depth_points=None):
+    """aggregate_2d_features_ray_marching (rm.py:260-307) fused with switch_pointcloud (rm.py:339-407): the march
+    runs as usual, M is read back, the keep mask is drawn (or taken from `masks`), and the fill kernel produces ONLY
+    the kept rows, offset already added -- the un-sampled point cloud (M x (3+C) floats) is never written.
+
+    Returns (coords list of [Nsel,3], features list of [Nsel,C]) like switch_pointcloud."""
+    _check_mode(mode, threshold, depth_points)
+    lib = _lib.load()
+    view_list = _as_view_list(features)
+    fs = _FeatureStack(view_list, need_vector_layout=False)
+    device = fs.device
+    if not isinstance(projections, torch.Tensor):
+        projections = torch.stack(list(projections), dim=0)
+    P_scaled = scale_projections(projections, stride)
+    grid = _lib.make_grid(voxel_dim, voxel_size, _origin3(origin))
+    coords, feats = [], []
+    with torch.cuda.device(device):
+        for b in range(fs.B):
+            m = _march(fs, b, P_scaled[:, b], tsdf[b, 0], grid, voxel_dim, voxel_size, grids, mode, threshold,
+                       depth_points)
+            desc = fs.descriptor(b)
+            n = int(_read_result(m).rows)
+            mask = masks[b] if masks is not None else (sample_points(n, max_points, rng) if max_points is not None
+                                                       else None)
+            if mask is None:
+                mask_dev, n_sel = torch.ones(n, dtype=torch.bool, device=device), n
+            else:
+                n_sel = int(mask.sum())
+                mask_dev = _to_mask_dev(mask, n, device)
+            cols = fs.C + 3
+            out = torch.empty((n_sel, cols), dtype=torch.float32, device=device)
+            if n_sel > 0:
+                prefix, _kept = _mask_prefix(mask_dev)
+                off3 = (C.c_float * 3)(*_origin3(offsets[b]))
+                _lib.check(lib.cnrma_rma_fill_selected(
+                    C.byref(grid), C.c_void_p(m.pinv.data_ptr()), C.byref(desc), m.grids, m.t_one, m.mode, m.threshold,
+                    m.depth_points, C.c_void_p(m.workspace.data_ptr()), C.c_void_p(m.result.data_ptr()), 1, None,
+                    C.c_void_p(mask_dev.data_ptr()), C.c_void_p(prefix.data_ptr()), off3, C.c_void_p(out.data_ptr()),
+                    cols, n_sel, _stream(device)), "cnrma_rma_fill_selected")
+            coords.append(out[:, 0:3])
+            feats.append(out[:, 3:])
+    return coords, feats

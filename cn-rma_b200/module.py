@@ -22,7 +22,7 @@ from . import functional as F
 
 class RayMarchingAggregator:
     def __init__(self, voxel_size, voxel_dim, origin=(0, 0, 0), backbone2d_stride=4, ray_marching_type="neus",
-                 neus_threshold=None, depth_points=None):
+                 neus_threshold=None, depth_points=None, max_points=None, feature_transform=None):
         self.voxel_size = voxel_size
         self.voxel_dim = tuple(voxel_dim)
         self.origin = torch.tensor(origin).view(1, 3)         # rm.py:184
@@ -30,6 +30,8 @@ class RayMarchingAggregator:
         self.ray_marching_type = ray_marching_type
         self.neus_threshold = neus_threshold
         self.depth_points = depth_points
+        self.max_points = max_points                  # rm.py:182
+        self.feature_transform = feature_transform    # rm.py:158-161 (augmentation: the caller's callable)
         if ray_marching_type == "neus":                        # rm.py:191-194
             assert neus_threshold is not None
         elif ray_marching_type == "depth":
@@ -112,6 +114,21 @@ class RayMarchingAggregator:
                                 mode="depth", depth_points=select_grids)
 
 
+    # ---- hand-off -----------------------------------------------------------------------------------
+    def switch_pointcloud(self, points, gt_bboxes, offsets, test):
+        """rm.py:339-407: `coord + offset`, sample_points' mask (numpy RNG on the host, as in the reference), ordered
+        selection of whole rows on the device, then the caller's augmentation.  Returns (coords, features, boxes)."""
+        coords, feats = F.switch_pointcloud(points, offsets, max_points=self.max_points)
+        new_boxes = []
+        for b in range(len(points)):
+            if self.feature_transform is not None and not test:
+                coords[b], box = self.feature_transform(coords[b], gt_bboxes[b])
+            else:
+                box = gt_bboxes[b]
+            new_boxes.append(box)
+        return coords, feats, new_boxes
+
+
 def make_detector_class(ray_marching_cls):
     """mmdet adapter: `RayMarchingB200 = make_detector_class(RayMarching)` gives a detector whose five
     aggregation methods and three state attributes come from RayMarchingAggregator while everything else
@@ -126,6 +143,7 @@ def make_detector_class(ray_marching_cls):
         aggregate_2d_features_ray_marching = RayMarchingAggregator.aggregate_2d_features_ray_marching
         ray_projection_neus = RayMarchingAggregator.ray_projection_neus
         ray_projection_depth = RayMarchingAggregator.ray_projection_depth
+        switch_pointcloud = RayMarchingAggregator.switch_pointcloud
         # `volume` / `valid` are assigned by the parent's initialize_volume; the properties take over
         volume = property(RayMarchingAggregator.volume.fget, lambda self, v: None)
         valid = property(RayMarchingAggregator.valid.fget, lambda self, v: None)

@@ -199,6 +199,35 @@ int cnrma_rma_fill_backward(const cnrma_grid *grid, const cnrma_features *grad_f
                             float threshold, int depth_points, const void *workspace, const cnrma_rma_result *result,
                             int normalize, const float *mean, const float *grad_rows, int64_t row_stride, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Point-cloud hand-off (RayMarching.switch_pointcloud, rm.py:339-407): `coord + offset` and the sub-sampling mask of
+ * sample_points (datasets/pipelines/fcaf3d_transforms.py:283-296, max_points) applied to whole rows in one ordered
+ * compaction instead of one torch.masked_select per column (rm.py:380-402).  The mask itself is an input: the
+ * reference draws it with numpy's RNG on the host, and only the same mask gives the same rows.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Bytes of scratch for cnrma_mask_prefix over `rows` rows. */
+int cnrma_handoff_workspace_bytes(int64_t rows, size_t *bytes);
+
+/* prefix[i] = number of kept rows before row i (int32 [rows]); *kept (device int64) = total kept. */
+int cnrma_mask_prefix(const uint8_t *mask, int64_t rows, void *workspace, size_t workspace_bytes, int32_t *prefix,
+                      int64_t *kept, void *stream);
+
+/* out[prefix[i], :] = rows[i, :] for every kept row i, with offset_host[0..2] added to columns 0..2.
+ * rows f32 [n_rows, row_stride] (first `cols` columns used), out f32 [capacity, out_stride]. */
+int cnrma_select_rows(const float *rows, int64_t row_stride, int cols, int64_t n_rows, const uint8_t *mask,
+                      const int32_t *prefix, const float *offset_host, float *out, int64_t out_stride,
+                      int64_t capacity, void *stream);
+
+/* cnrma_rma_fill fused with the hand-off: only the kept rows are produced (at out row prefix[row], offset added),
+ * i.e. aggregate_2d_features_ray_marching + switch_pointcloud in one pass.  mask / prefix index the M rows of the
+ * march in their (view, v, u, step) order. */
+int cnrma_rma_fill_selected(const cnrma_grid *grid, const float *pinv, const cnrma_features *features, int grids,
+                            float t_one, int mode, float threshold, int depth_points, const void *workspace,
+                            const cnrma_rma_result *result, int normalize, const float *mean, const uint8_t *mask,
+                            const int32_t *prefix, const float *offset_host, float *rows, int64_t row_stride,
+                            int64_t capacity, void *stream);
+
 /* Dense per-sample view of the march records for parity tests: weights f32 [V*H*W*N] (0 where not kept,
  * i.e. rm.py:767 `weights * valid_final`) and keep uint8 [V*H*W*N].  NEUS mode only. */
 int cnrma_rma_expand(int views, int height, int width, int grids, float threshold, const void *workspace,

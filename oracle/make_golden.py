@@ -13,6 +13,7 @@ Each fixture stores the inputs and what the reference's own code returns for the
            rm.py:260-307 aggregate_2d_features_ray_marching -> points [M, 3+C];
            rm.py:809-956 ray_projection_depth for depth_points 0..2 through the same aggregate call.
            Also the intermediates rm.py:71-111 (o, d) of view 0.
+  Hand-off rm.py:339-407 switch_pointcloud (+ sample_points mask, numpy seed 2024) on the NeuS points.
   Grads    d(sum(volume * G)) / d features and d(sum(points * G')) / d features from the reference's own autograd.
 
 The fixtures are the pin for oracle/cnrma_oracle.c (tests/test_oracle_golden.py) and a second
@@ -189,6 +190,21 @@ def run_case(name, sc, opt):
     (pts_g * g_pts).sum().backward()
     out["grad_points"] = g_pts.numpy()
     out["grad_features_stage_b"] = fg.grad[:, 0].numpy().copy()
+
+    # ---- hand-off: the reference's switch_pointcloud (rm.py:339-407) on the points above, max_points = M // 3
+    sh = ref_shim.make_self(sc.voxel_dim, sc.voxel_size, origin, stride=stride, neus_threshold=thr)
+    sh.max_points = max(1, out["neus_points"].shape[0] // 3)
+    sh.feature_transform = None
+    sh.switch_pointcloud = __import__("types").MethodType(rm.RayMarching.switch_pointcloud, sh)
+    offset = torch.tensor([0.37, -1.25, 0.5])
+    np.random.seed(2024)
+    sel_c, sel_f, _ = sh.switch_pointcloud([torch.from_numpy(out["neus_points"])], [None], [offset], True)
+    np.random.seed(2024)
+    out["handoff_mask"] = rm.sample_points(torch.from_numpy(out["neus_points"])[:, 0:3], max_points=sh.max_points).numpy()
+    out["handoff_offset"] = offset.numpy()
+    out["handoff_max_points"] = np.int64(sh.max_points)
+    out["handoff_coords"] = sel_c[0].numpy()
+    out["handoff_features"] = sel_f[0].numpy()
 
     path = os.path.join(ROOT, "tests", "golden", name + ".npz")
     np.savez_compressed(path, **out)
