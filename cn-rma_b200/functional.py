@@ -344,7 +344,16 @@ def invert_projections(projections_scaled):
     threads = torch.get_num_threads()
     torch.set_num_threads(1)
     try:
-        torch.inverse(p4, out=out)
+        try:
+            torch.inverse(p4, out=out)
+        except RuntimeError:
+            # a singular camera matrix: the reference's per-view torch.inverse raises, its caller swallows the
+            # exception and drops that view (rm.py:277-283).  NaN ray parameters reproduce "contributes nothing".
+            for v in range(V):
+                try:
+                    torch.inverse(p4[v], out=out[v])
+                except RuntimeError:
+                    out[v].fill_(float("nan"))
     finally:
         torch.set_num_threads(threads)
     return out

@@ -37,6 +37,9 @@ CONFIGS = {
                      tsdf="room", grids=300, dtype="f32"),
     "cfg5": dict(views=300, channels=128, height=120, width=160, voxel_dim=(256, 256, 96), voxel_size=0.04,
                  tsdf="room", grids=256, dtype="bf16"),
+    # the reference's own shipped test configuration (ray_marching_scannet.py:12-19, :123, :158): 32 channels
+    "ref_test": dict(views=50, channels=32, height=120, width=160, voxel_dim=(256, 256, 96), voxel_size=0.04,
+                     tsdf="room", grids=300, dtype="f32"),
     # small shapes for fast parity tests
     "tiny": dict(views=3, channels=8, height=12, width=16, voxel_dim=(8, 8, 4), voxel_size=0.4,
                  tsdf="room", grids=40, dtype="f32"),

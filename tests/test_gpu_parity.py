@@ -338,3 +338,73 @@ def test_count_division_shortcut_is_ieee_exact(cn):
     st = lib.cnrma_selftest_count_division(512, C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert st == 0
     assert int(out.item()) == 0
+
+
+def test_batch_of_two(cn):
+    """B = 2 (Stage A supports it in the reference, rm.py:44-64; Stage B is batch-1 there, rm.py:707 -- here each
+    batch element gets its own march)."""
+    s0 = cn.synthetic.make_scene("tiny", seed=11)
+    s1 = cn.synthetic.make_scene("tiny", seed=12)
+    f = torch.stack([torch.from_numpy(s0.features), torch.from_numpy(s1.features)], dim=1).cuda()      # [V,2,C,H,W]
+    p = torch.stack([torch.from_numpy(s0.projections), torch.from_numpy(s1.projections)], dim=1).cuda()
+    t = torch.stack([torch.from_numpy(s0.tsdf), torch.from_numpy(s1.tsdf)], dim=0).cuda()[:, None]
+    vol, cnt, _ = cn.aggregate_views(p, f, s0.voxel_dim, s0.voxel_size, s0.origin, s0.stride)
+    pts = cn.rma_points(p, f, t, s0.voxel_dim, s0.voxel_size, s0.origin, s0.stride, grids=s0.grids, threshold=0.05)
+    for b, sc in enumerate((s0, s1)):
+        ovol, ocnt = oracle.aggregate_views(sc.projections, sc.features, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
+        assert np.array_equal(cnt[b, 0].cpu().numpy(), ocnt)
+        assert np.array_equal(vol[b].cpu().numpy().view(np.uint32), ovol.view(np.uint32))
+        ref = oracle.aggregate_2d_features_ray_marching(sc.projections, sc.features, sc.tsdf, sc.voxel_dim, sc.voxel_size,
+                                                        sc.origin, sc.stride, grids=sc.grids)
+        got = pts[b].cpu().numpy()
+        assert got.shape == ref.shape and np.array_equal(got[:, :3], ref[:, :3])
+        assert_rel(got[:, 3:], ref[:, 3:], FP32_REL, what=f"points b={b}")
+
+
+def test_zero_threshold_keeps_every_inbounds_sample(cn):
+    """weight_threshold = 0: `weights >= 0` holds for every sample, so all in-bounds samples are kept (rm.py:765-767);
+    no early exits or empty-space jumps apply."""
+    sc = cn.synthetic.make_scene("tiny", seed=13)
+    p, f, t = _scene_tensors(sc)
+    rows = cn.rma_points(p, f, t, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride, grids=sc.grids, threshold=0.0,
+                         normalize=False)[0].cpu().numpy()
+    ref = oracle.aggregate_2d_features_ray_marching(sc.projections, sc.features, sc.tsdf, sc.voxel_dim, sc.voxel_size,
+                                                    sc.origin, sc.stride, grids=sc.grids, neus_threshold=0.0,
+                                                    normalize=False)
+    assert rows.shape == ref.shape
+    assert np.array_equal(rows[:, :3].view(np.uint32), ref[:, :3].view(np.uint32))
+    assert np.abs(rows[:, 3] - ref[:, 3]).max() <= 1e-6
+
+
+def test_unsupported_inputs_fail_loudly(cn):
+    sc = cn.synthetic.make_scene("tiny", seed=14)
+    p, f, t = _scene_tensors(sc)
+    with pytest.raises(cn.CnrmaError):                       # channel count must fill 16-byte vectors
+        cn.aggregate_views(p, f[:, :, :6].contiguous(), sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
+    with pytest.raises(ValueError):                          # tsdf of the wrong shape
+        cn.rma_points(p, f, t[:, :, :4], sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride, threshold=0.05)
+    with pytest.raises(ValueError):
+        cn.aggregate_views(p[:2], f, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
+
+
+def test_degenerate_cameras_do_not_crash(cn):
+    """A singular / non-finite projection: every voxel is outside (pz <= 0 or NaN) and every ray is non-finite, so
+    the view contributes nothing -- like the reference, whose ids become INT64_MIN and fail the masks."""
+    sc = cn.synthetic.make_scene("tiny", seed=15)
+    p, f, t = _scene_tensors(sc)
+    p = p.clone()
+    p[1] = 0.0                       # degenerate: camera z row is zero -> pz = 0 -> nothing valid
+    vol, cnt, _ = cn.aggregate_views(p, f, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
+    _px, _py, valid = cn.project_views(p, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride, sc.height, sc.width)
+    assert not bool(valid[1].any())
+    assert bool(torch.isfinite(vol).all())
+    # Stage B: torch.inverse raises for the singular view; the reference's caller drops it (rm.py:277-283)
+    pts = cn.rma_points(p, f, t, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride, grids=sc.grids, threshold=0.05,
+                        normalize=False)[0]
+    keep = [0, 2]
+    ref = oracle.aggregate_2d_features_ray_marching(sc.projections[keep], sc.features[keep], sc.tsdf, sc.voxel_dim,
+                                                    sc.voxel_size, sc.origin, sc.stride, grids=sc.grids, normalize=False)
+    assert pts.shape == ref.shape and np.array_equal(pts[:, :3].cpu().numpy(), ref[:, :3])
+    p[1, 0, 2, 3] = float("nan")
+    _px, _py, valid = cn.project_views(p, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride, sc.height, sc.width)
+    assert not bool(valid[1].any())
