@@ -11,7 +11,8 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libcnrma_b200.so")
-SOURCES = ["cnrma_abi.cu", "cnrma_stage_a.cu", "cnrma_stage_b.cu", "cnrma_backward.cu", "cnrma_handoff.cu"]
+SOURCES = ["cnrma_abi.cu", "cnrma_stage_a.cu", "cnrma_stage_a_list.cu", "cnrma_stage_b.cu", "cnrma_backward.cu",
+           "cnrma_handoff.cu"]
 HEADERS = ["cnrma_common.cuh", "cnrma_internal.cuh", os.path.join("..", "..", "include", "cnrma_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

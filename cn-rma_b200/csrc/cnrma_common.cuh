@@ -38,19 +38,42 @@ __device__ __forceinline__ float row_dot4(float p0, float p1, float p2, float p3
     return acc;
 }
 
+// round(cx / cz) and round(cy / cz) (rm.py:52-53: IEEE division, half-to-even).  Only the rounded integers are
+// needed, so the two divisions are replaced by one correctly rounded reciprocal and two multiplications whenever that
+// provably cannot change the result: q = RN(c * RN(1/cz)) is within |q| * 2^-23 of the exact quotient, hence
+// rint(q) == rint(RN(c / cz)) unless q lies within |q| * 2^-21 of a half-integer -- then (and for NaN / inf / huge
+// quotients) the divisions are done for real.
+__device__ __forceinline__ void rounded_pixel(float cx, float cy, float cz, float &rx, float &ry) {
+    const float r = __frcp_rn(cz);
+    const float qx = __fmul_rn(cx, r), qy = __fmul_rn(cy, r);
+    rx = rintf(qx);
+    ry = rintf(qy);
+    const bool safe = (fabsf(__fsub_rn(qx, rx)) < __fmaf_rn(fabsf(qx), -4.76837158203125e-07f, 0.5f)) &&
+                      (fabsf(__fsub_rn(qy, ry)) < __fmaf_rn(fabsf(qy), -4.76837158203125e-07f, 0.5f));
+    if (!safe) {
+        rx = rintf(__fdiv_rn(cx, cz));
+        ry = rintf(__fdiv_rn(cy, cz));
+    }
+}
+
+// Frustum test of rm.py:58 on the rounded pixel coordinates.  The reference converts to int64 and compares; comparing
+// the integer-valued floats is equivalent for every finite value, and NaN / +-inf (which x86 turns into INT64_MIN)
+// fail the test either way.
+__device__ __forceinline__ bool in_frustum(float rx, float ry, float cz, int H, int W) {
+    return (rx >= 0.0f) && (ry >= 0.0f) && (rx < (float)W) && (ry < (float)H) && (cz > 0.0f);
+}
+
 // One voxel through one stride-scaled projection (rm.py:48-58).  P points at 12 floats with element
 // stride `ps` (shared memory, structure-of-arrays over views).  Returns true when the voxel is inside
-// the view frustum; px/py are the rounded pixel coordinates (exact integers as floats).
+// the view frustum; px/py are the rounded pixel coordinates.
 __device__ __forceinline__ bool project_voxel(const float *P, int ps, float wx, float wy, float wz, int H, int W,
                                               int &px, int &py) {
     const float cx = row_dot4(P[0 * ps], P[1 * ps], P[2 * ps], P[3 * ps], wx, wy, wz, 1.0f);
     const float cy = row_dot4(P[4 * ps], P[5 * ps], P[6 * ps], P[7 * ps], wx, wy, wz, 1.0f);
     const float cz = row_dot4(P[8 * ps], P[9 * ps], P[10 * ps], P[11 * ps], wx, wy, wz, 1.0f);
-    const float rx = rintf(__fdiv_rn(cx, cz));  // Tensor.round() is half-to-even
-    const float ry = rintf(__fdiv_rn(cy, cz));
-    // The reference converts to int64 and compares; comparing the integer-valued floats is equivalent for
-    // every finite value, and NaN / +-inf (which x86 turns into INT64_MIN) fail the test either way.
-    const bool ok = (rx >= 0.0f) && (ry >= 0.0f) && (rx < (float)W) && (ry < (float)H) && (cz > 0.0f);
+    float rx, ry;
+    rounded_pixel(cx, cy, cz, rx, ry);
+    const bool ok = in_frustum(rx, ry, cz, H, W);
     px = ok ? (int)rx : 0;
     py = ok ? (int)ry : 0;
     return ok;

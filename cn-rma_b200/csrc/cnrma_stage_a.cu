@@ -282,6 +282,14 @@ static cudaError_t run_aggregate(const AggParams &p_in, int dtype, int max_chunk
 cudaError_t run_aggregate_views(const GridDev &g, const cnrma_features &f, int v0, int nv, const float *proj,
                                 int64_t proj_stride, float stride, uint32_t flags, float *volume, int64_t vsv,
                                 int64_t vsc, int32_t *count, uint8_t *valid, int max_chunk_bytes, cudaStream_t stream) {
+    // Kernel choice (DESIGN.md "K_A"): rows of 512 bytes and more go through the TMA kernel below (DRAM-bound, deep
+    // register-free gather queue); shorter rows -- and the finalise-only pass -- through the list kernel
+    // (cnrma_stage_a_list.cu), whose lane <-> voxel projection needs a third of the instructions.
+    const int row_bytes = f.channels * ((f.dtype == CNRMA_BF16) ? 2 : 4);
+    bool use_list = row_bytes < 512 || nv == 0;
+    if (const char *env = std::getenv("CNRMA_AGG_KERNEL")) use_list = (env[0] == 'l');   // tuning aid: "list" / "tma"
+    if (use_list && list_kernel_supports(nv, f.height, f.width))
+        return run_aggregate_list(g, f, v0, nv, proj, proj_stride, stride, flags, volume, vsv, vsc, count, valid, stream);
     AggParams p;
     p.g = g;
     p.V = nv;

@@ -1,0 +1,276 @@
+// Stage A, list kernel: the same fused back-projection as cnrma_stage_a.cu (bit-identical results), organised for
+// instruction economy.  It serves feature rows below 512 bytes -- the reference's own 32-channel maps are 128-byte
+// rows -- and scenes with many more voxels than pixels, where the TMA kernel's per-voxel projection rounds and
+// per-row issue / drain overhead, not DRAM, set the time (ref test config, 256x256x96 x 50 views x 32 ch: 6.5 ms).
+//
+//   phase 1  lane <-> voxel: a warp takes a batch of up to 32 consecutive voxels of the z-slice sweep and walks the
+//            views in order; the camera matrix of the current view is warp-uniform (broadcast shared-memory reads),
+//            every lane projects its own voxel and appends the pixel of each view that sees it to its voxel's list in
+//            shared memory.  One projection serves 32 voxels: ~1.2 warp instructions per (voxel, view) instead of ~3.
+//   phase 2  lane group <-> voxel: groups of G = row_bytes/16/VPL lanes walk the lists (kept in view order, so the
+//            fp32 sums are formed exactly like the reference's `self.volume + volume` loop), 32/G voxels at a time,
+//            with coalesced 16-byte loads of the channels-last rows, U rows in flight per group before the first add.
+#include <cstdlib>
+
+#include "cnrma_internal.cuh"
+
+namespace cnrma {
+
+struct ListParams {
+    GridDev g;
+    int V, C, H, W, nvox;
+    int64_t stride_y_bytes, stride_x_bytes;
+    float stride;
+    const float *proj;
+    int64_t proj_stride;
+    float *volume;
+    int64_t vsv, vsc;
+    int32_t *count;
+    uint8_t *valid;
+    uint32_t flags;
+    int vec_store;
+    int chunk_base, write_count;
+    int nb;     // voxels per warp batch (<= 32)
+    int lcap;   // list capacity per voxel (odd, >= V)
+    const void *views[kMaxViewsPerLaunch];
+};
+
+constexpr int kListThreads = 256;
+constexpr int kListUnroll = 4;
+
+template <int G, int VPL, typename T>
+__global__ void __launch_bounds__(kListThreads) aggregate_views_list_kernel(const __grid_constant__ ListParams p) {
+    using V16 = Vec16<T>;
+    constexpr int E = V16::kElems;
+    constexpr int kWarps = kListThreads / kWarp;
+    constexpr int kVPW = kWarp / G;   // voxels gathered concurrently by one warp
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *sP = reinterpret_cast<float *>(smem_raw);                                                    // [V][12]
+    const unsigned char **sView = reinterpret_cast<const unsigned char **>(smem_raw + sizeof(float) * 12 * p.V);   // [V]
+    uint32_t *sList = reinterpret_cast<uint32_t *>(smem_raw + sizeof(float) * 12 * p.V + sizeof(void *) * p.V);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *my_lists = sList + (size_t)warp * p.nb * p.lcap;
+
+    for (int i = threadIdx.x; i < 12 * p.V; i += blockDim.x) {
+        const int v = i / 12, k = i % 12;
+        float val = __ldg(p.proj + (int64_t)v * p.proj_stride + k);
+        if (k < 8) val = __fdiv_rn(val, p.stride);   // rows 0-1 / stride (rm.py:238-239)
+        sP[i] = val;
+    }
+    const int chunk = p.chunk_base + blockIdx.y;
+    constexpr int kChunkBytes = G * VPL * 16;
+    for (int i = threadIdx.x; i < p.V; i += blockDim.x)
+        sView[i] = static_cast<const unsigned char *>(p.views[i]) + (size_t)chunk * kChunkBytes;
+    __syncthreads();
+
+    const int grp = lane / G, lig = lane % G;
+    const int c0 = chunk * (kChunkBytes / (int)sizeof(T)) + lig * E;   // first channel of this lane (+ q*G*E)
+    const int nxy = p.g.nx * p.g.ny;
+    const float inv_nxy = 1.0f / (float)nxy, inv_ny = 1.0f / (float)p.g.ny;
+    const int units = (p.nvox + p.nb - 1) / p.nb;
+    const int warps_total = gridDim.x * kWarps;
+
+    for (int u = blockIdx.x * kWarps + warp; u < units; u += warps_total) {
+        // ---- phase 1: lane <-> voxel -------------------------------------------------------------------------
+        const int it = u * p.nb + lane;                       // z-slice sweep index
+        const bool active = lane < p.nb && it < p.nvox;
+        int vz, rem, vx, vy;
+        fast_divmod(active ? it : 0, nxy, inv_nxy, vz, rem);
+        fast_divmod(rem, p.g.ny, inv_ny, vx, vy);
+        const int vox = (vx * p.g.ny + vy) * p.g.nz + vz;    // voxel order of datasets/tsdf.py:24-29
+        const float wx = world_coord(vx, p.g.vs, p.g.ox);
+        const float wy = world_coord(vy, p.g.vs, p.g.oy);
+        const float wz = world_coord(vz, p.g.vs, p.g.oz);
+        uint32_t *lst = my_lists + lane * p.lcap;
+        int cnt = 0;
+        for (int v = 0; v < p.V; ++v) {
+            const float4 a = *reinterpret_cast<const float4 *>(sP + 12 * v);       // warp-uniform: broadcast reads
+            const float4 b = *reinterpret_cast<const float4 *>(sP + 12 * v + 4);
+            const float4 c = *reinterpret_cast<const float4 *>(sP + 12 * v + 8);
+            const float cx = row_dot4(a.x, a.y, a.z, a.w, wx, wy, wz, 1.0f);
+            const float cy = row_dot4(b.x, b.y, b.z, b.w, wx, wy, wz, 1.0f);
+            const float cz = row_dot4(c.x, c.y, c.z, c.w, wx, wy, wz, 1.0f);
+            float rx, ry;
+            rounded_pixel(cx, cy, cz, rx, ry);
+            if (active && in_frustum(rx, ry, cz, p.H, p.W))
+                lst[cnt++] = ((uint32_t)v << 20) | ((uint32_t)(int)ry << 10) | (uint32_t)(int)rx;
+        }
+        __syncwarp();
+
+        // ---- phase 2: lane group <-> voxel ---------------------------------------------------------------------
+        for (int b0 = 0; b0 < p.nb; b0 += kVPW) {
+            const int j = b0 + grp;                                       // voxel (lane of phase 1) of this group
+            const int jcnt = __shfl_sync(0xffffffffu, cnt, j & 31);
+            const int jvox = __shfl_sync(0xffffffffu, vox, j & 31);
+            const bool jact = __shfl_sync(0xffffffffu, (int)active, j & 31) != 0 && j < p.nb;
+            const int n = jact ? jcnt : 0;
+            const uint32_t *jl = my_lists + (j < p.nb ? j : 0) * p.lcap;
+            float acc[VPL][E];
+            int total = n;
+            if ((p.flags & CNRMA_AGG_ACCUMULATE) && jact) {
+                total += (p.flags & CNRMA_AGG_COUNT_F32) ? (int)reinterpret_cast<const float *>(p.count)[jvox] : p.count[jvox];
+#pragma unroll
+                for (int q = 0; q < VPL; ++q)
+#pragma unroll
+                    for (int e = 0; e < E; ++e)
+                        acc[q][e] = p.volume[(int64_t)jvox * p.vsv + (int64_t)(c0 + q * G * E + e) * p.vsc];
+            } else {
+#pragma unroll
+                for (int q = 0; q < VPL; ++q)
+#pragma unroll
+                    for (int e = 0; e < E; ++e) acc[q][e] = 0.0f;
+            }
+            int nmax = n;   // longest list among the groups of this warp
+#pragma unroll
+            for (int o = 16; o >= G; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+            for (int k = 0; k < nmax; k += kListUnroll) {
+                V16 val[kListUnroll][VPL];
+#pragma unroll
+                for (int uu = 0; uu < kListUnroll; ++uu) {
+                    if (k + uu < n) {
+                        const uint32_t e = jl[k + uu];
+                        const unsigned char *src = sView[e >> 20] + (int64_t)((e >> 10) & 1023u) * p.stride_y_bytes +
+                                                   (int64_t)(e & 1023u) * p.stride_x_bytes + lig * 16;
+#pragma unroll
+                        for (int q = 0; q < VPL; ++q) val[uu][q] = V16::load(reinterpret_cast<const T *>(src + q * G * 16));
+                    }
+                }
+#pragma unroll
+                for (int uu = 0; uu < kListUnroll; ++uu) {
+                    if (k + uu < n) {
+#pragma unroll
+                        for (int q = 0; q < VPL; ++q)
+#pragma unroll
+                            for (int e = 0; e < E; ++e) acc[q][e] = __fadd_rn(acc[q][e], val[uu][q].v[e]);
+                    }
+                }
+            }
+            if (!jact) continue;
+            if (p.flags & CNRMA_AGG_MEAN) {
+                const float fn = (float)total;   // rm.py:251: fp32 sum / int64 count, 0 where count == 0
+                const float y = __frcp_rn(fn);
+#pragma unroll
+                for (int q = 0; q < VPL; ++q)
+#pragma unroll
+                    for (int e = 0; e < E; ++e) acc[q][e] = (total > 0) ? div_by_count(acc[q][e], fn, y) : 0.0f;
+            }
+#pragma unroll
+            for (int q = 0; q < VPL; ++q) {
+                const int c = c0 + q * G * E;
+                if (p.vec_store) {
+                    float *dst = p.volume + (int64_t)jvox * p.vsv + c;
+#pragma unroll
+                    for (int e = 0; e < E; e += 4)
+                        __stcs(reinterpret_cast<float4 *>(dst + e), make_float4(acc[q][e], acc[q][e + 1], acc[q][e + 2], acc[q][e + 3]));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) p.volume[(int64_t)jvox * p.vsv + (int64_t)(c + e) * p.vsc] = acc[q][e];
+                }
+            }
+            if (lig == 0 && blockIdx.y == 0 && p.write_count) {
+                if (p.flags & CNRMA_AGG_COUNT_F32) reinterpret_cast<float *>(p.count)[jvox] = (float)total;
+                else p.count[jvox] = total;
+                if (p.valid != nullptr) p.valid[jvox] = (uint8_t)(total > 0);
+            }
+        }
+        __syncwarp();   // the lists are rewritten by the next unit
+    }
+}
+
+// ---- launch -----------------------------------------------------------------------------------------------------
+
+template <int G, int VPL, typename T>
+static cudaError_t launch_list(const ListParams &p, int chunks, cudaStream_t stream) {
+    const size_t smem = sizeof(float) * 12 * p.V + sizeof(void *) * p.V +
+                        sizeof(uint32_t) * (size_t)(kListThreads / kWarp) * p.nb * p.lcap;
+    auto kernel = aggregate_views_list_kernel<G, VPL, T>;
+    struct Cached { int dev = -1; size_t smem = 0; int ctas = 0; };
+    static thread_local Cached cache;
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    if (cache.dev != dev || cache.smem != smem) {
+        err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        int sms = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kListThreads, smem);
+        if (err != cudaSuccess) return err;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        cache.dev = dev;
+        cache.smem = smem;
+        cache.ctas = sms * per_sm;
+    }
+    const int units = (p.nvox + p.nb - 1) / p.nb;
+    const int needed = (units + (kListThreads / kWarp) - 1) / (kListThreads / kWarp);
+    const dim3 grid(needed < cache.ctas ? needed : cache.ctas, chunks);
+    kernel<<<grid, kListThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t launch_list_gv(const ListParams &p, int g, int vpl, int chunks, cudaStream_t stream) {
+#define CNRMA_LIST_CASE(GG, VV) \
+    if (g == GG && vpl == VV) return launch_list<GG, VV, T>(p, chunks, stream);
+    CNRMA_LIST_CASE(1, 1) CNRMA_LIST_CASE(2, 1) CNRMA_LIST_CASE(4, 1) CNRMA_LIST_CASE(8, 1) CNRMA_LIST_CASE(16, 1)
+    CNRMA_LIST_CASE(32, 1) CNRMA_LIST_CASE(32, 2) CNRMA_LIST_CASE(1, 3) CNRMA_LIST_CASE(2, 3) CNRMA_LIST_CASE(4, 3)
+    CNRMA_LIST_CASE(8, 3) CNRMA_LIST_CASE(16, 3) CNRMA_LIST_CASE(32, 3) CNRMA_LIST_CASE(32, 4)
+#undef CNRMA_LIST_CASE
+    return cudaErrorInvalidValue;
+}
+
+// True when the list kernel can serve this shape (pixel coordinates and view ids are packed into 32 bits).
+bool list_kernel_supports(int V, int H, int W) { return V <= 4096 && H <= 1024 && W <= 1024 && V <= kMaxViewsPerLaunch; }
+
+cudaError_t run_aggregate_list(const GridDev &g, const cnrma_features &f, int v0, int nv, const float *proj,
+                               int64_t proj_stride, float stride, uint32_t flags, float *volume, int64_t vsv, int64_t vsc,
+                               int32_t *count, uint8_t *valid, cudaStream_t stream) {
+    const int esz = (f.dtype == CNRMA_BF16) ? 2 : 4;
+    const int nvec = f.channels * esz / 16;
+    // lanes per voxel: the largest power of two <= 32 dividing nvec; the rest as vectors per lane (<= 4) and chunks
+    int G = 1;
+    while (G < 32 && nvec % (G * 2) == 0) G *= 2;
+    const int q = nvec / G;
+    int vpl = 1;
+    for (int d = 4; d >= 1; --d)
+        if (q % d == 0 && (d == 1 || d == 3 || G == 32)) { vpl = d; break; }
+    const int chunks = q / vpl;
+    ListParams p;
+    p.g = g;
+    p.V = nv; p.C = f.channels; p.H = f.height; p.W = f.width;
+    p.nvox = g.nx * g.ny * g.nz;
+    p.stride_y_bytes = f.stride_y * esz;
+    p.stride_x_bytes = f.stride_x * esz;
+    p.stride = stride;
+    p.proj = proj;
+    p.proj_stride = proj_stride;
+    p.volume = volume;
+    p.vsv = vsv; p.vsc = vsc;
+    p.count = count;
+    p.valid = valid;
+    p.flags = flags;
+    p.vec_store = (vsc == 1) && (vsv % 4 == 0) && (reinterpret_cast<uintptr_t>(volume) % 16 == 0);
+    p.lcap = nv | 1;                                      // odd: the lanes' list writes hit different banks
+    int nb = 32;                                          // voxels per warp batch: lists must fit ~8 KB per warp
+    while (nb > 1 && (size_t)nb * p.lcap * 4 > 8192) nb >>= 1;
+    if (nb < 32 / G) nb = 32 / G;                         // at least one full gather round
+    p.nb = nb;
+    for (int i = 0; i < nv; ++i) p.views[i] = f.view_ptrs_host[v0 + i];
+    auto launch = [&](const ListParams &lp, int nchunks) -> cudaError_t {
+        return (f.dtype == CNRMA_BF16) ? launch_list_gv<__nv_bfloat16>(lp, G, vpl, nchunks, stream)
+                                       : launch_list_gv<float>(lp, G, vpl, nchunks, stream);
+    };
+    p.chunk_base = 0;
+    p.write_count = 1;
+    if (!(flags & CNRMA_AGG_ACCUMULATE) || chunks == 1) return launch(p, chunks);
+    for (int c = 0; c < chunks; ++c) {   // see run_aggregate in cnrma_stage_a.cu: the count is rewritten by the last chunk only
+        p.chunk_base = c;
+        p.write_count = (c == chunks - 1);
+        const cudaError_t err = launch(p, 1);
+        if (err != cudaSuccess) return err;
+    }
+    return cudaSuccess;
+}
+
+}  // namespace cnrma
