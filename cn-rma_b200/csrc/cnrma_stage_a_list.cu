@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(kListThreads) aggregate_views_list_kernel(cons
     const float inv_nxy = 1.0f / (float)nxy, inv_ny = 1.0f / (float)p.g.ny;
     const int units = (p.nvox + p.nb - 1) / p.nb;
     const int warps_total = gridDim.x * kWarps;
+    const float fW = (float)p.W - 0.5f, fH = (float)p.H - 0.5f;
 
     for (int u = blockIdx.x * kWarps + warp; u < units; u += warps_total) {
         // ---- phase 1: lane <-> voxel -------------------------------------------------------------------------
@@ -91,6 +92,14 @@ __global__ void __launch_bounds__(kListThreads) aggregate_views_list_kernel(cons
             const float cx = row_dot4(a.x, a.y, a.z, a.w, wx, wy, wz, 1.0f);
             const float cy = row_dot4(b.x, b.y, b.z, b.w, wx, wy, wz, 1.0f);
             const float cz = row_dot4(c.x, c.y, c.z, c.w, wx, wy, wz, 1.0f);
+            // Cheap superset of the frustum test on the un-divided coordinates: a visible voxel has cz > 0 and
+            // -0.5 <= cx/cz <= W-0.5, -0.5 <= cy/cz <= H-0.5 up to the rounding of the quotient, i.e.
+            // cx + 0.5 cz >= 0, (W-0.5) cz - cx >= 0, ... up to ~1e-7 cz; the slack used here is 1e-3 cz.  Neighbouring
+            // voxels mostly agree, so when no lane of the warp passes, the division / rounding / exact test is skipped.
+            const float slack = 1.0e-3f * cz;
+            const bool maybe = active && (cz > 0.0f) && (cx + 0.5f * cz >= -slack) && (fW * cz - cx >= -slack) &&
+                               (cy + 0.5f * cz >= -slack) && (fH * cz - cy >= -slack);
+            if (!__any_sync(0xffffffffu, maybe)) continue;
             float rx, ry;
             rounded_pixel(cx, cy, cz, rx, ry);
             if (active && in_frustum(rx, ry, cz, p.H, p.W))
