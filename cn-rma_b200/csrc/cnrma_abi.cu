@@ -161,7 +161,7 @@ int cnrma_rma_workspace_bytes(const cnrma_grid *grid, int views, int height, int
     if (!grid_ok(grid) || !bytes || views <= 0 || height <= 0 || width <= 0 || grids <= 0) return CNRMA_ERR_ARG;
     if (mode != CNRMA_MARCH_NEUS && mode != CNRMA_MARCH_DEPTH) return CNRMA_ERR_ARG;
     if (mode == CNRMA_MARCH_DEPTH && depth_points < 0) return CNRMA_ERR_ARG;
-    *bytes = rma_workspace(views, height, width, grids, mode, threshold, depth_points, rma_brick_count(to_dev(*grid)),
+    *bytes = rma_workspace(views, height, width, grids, mode, threshold, depth_points,
                            (int64_t)grid->nx * grid->ny * grid->nz).total;
     return CNRMA_OK;
 }
@@ -178,7 +178,7 @@ int cnrma_rma_march(const cnrma_grid *grid, const float *pinv, int views, int he
     const int d = device_ok();
     if (d != CNRMA_OK) return d;
     const RmaWorkspace ws = rma_workspace(views, height, width, grids, mode, threshold, depth_points,
-                                          rma_brick_count(to_dev(*grid)), (int64_t)grid->nx * grid->ny * grid->nz);
+                                          (int64_t)grid->nx * grid->ny * grid->nz);
     if (ws.blocks >= ((int64_t)1 << 31)) return CNRMA_ERR_UNSUPPORTED;
     const cudaError_t e = run_march(to_dev(*grid), pinv, views, height, width, tsdf, grids, t_one, mode, threshold,
                                     depth_points, workspace, ws, result, static_cast<cudaStream_t>(stream));
@@ -300,8 +300,7 @@ int cnrma_rma_fill_backward(const cnrma_grid *grid, const cnrma_features *grad_f
     const int d = device_ok();
     if (d != CNRMA_OK) return d;
     const RmaWorkspace ws = rma_workspace(grad_features->views, grad_features->height, grad_features->width, grids, mode,
-                                          threshold, depth_points, rma_brick_count(to_dev(*grid)),
-                                          (int64_t)grid->nx * grid->ny * grid->nz);
+                                          threshold, depth_points, (int64_t)grid->nx * grid->ny * grid->nz);
     const cudaError_t e = run_fill_backward(*grad_features, workspace, ws, normalize, mean ? mean : &result->mean,
                                             grad_rows, row_stride, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);

@@ -10,7 +10,7 @@ struct RmaWorkspace {
     int64_t rays;     // V*H*W
     int64_t blocks;   // ceil(rays / kRayThreads)
     int cap;          // (step, weight) records per ray
-    size_t off_counts, off_blk_rows, off_blk_wsum, off_blk_off, off_rec_w, off_rec_i, off_bricks, off_sigmoid, total;
+    size_t off_counts, off_blk_rows, off_blk_wsum, off_blk_off, off_rec_w, off_rec_i, off_dist, off_sigmoid, total;
 };
 
 // cnrma_stage_a.cu
@@ -29,8 +29,7 @@ cudaError_t run_to_channels_last(const void *src, int dtype, int C, int H, int W
 
 // cnrma_stage_b.cu
 RmaWorkspace rma_workspace(int views, int height, int width, int grids, int mode, float threshold, int depth_points,
-                           int64_t bricks = 0, int64_t nvox = 0);
-int64_t rma_brick_count(const GridDev &g);
+                           int64_t nvox = 0);
 cudaError_t run_march(const GridDev &g, const float *pinv, int V, int H, int W, const float *tsdf, int N, float t_one,
                       int mode, float thr, int depth_points, void *workspace, const RmaWorkspace &ws,
                       cnrma_rma_result *result, cudaStream_t stream);

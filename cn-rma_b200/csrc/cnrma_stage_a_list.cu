@@ -32,13 +32,17 @@ struct ListParams {
     int chunk_base, write_count;
     int nb;     // voxels per warp batch (<= 32)
     int lcap;   // list capacity per voxel (odd, >= V)
+    // uniform: the views are equally spaced in one allocation, so a list entry is the row's offset from views[0] in
+    // 16-byte units (one multiply-add to decode); otherwise entries pack (view, py, px) and go through the pointer table
+    int uniform;
+    uint32_t view_stride16, stride_y16, stride_x16;
     const void *views[kMaxViewsPerLaunch];
 };
 
 constexpr int kListThreads = 256;
 constexpr int kListUnroll = 4;
 
-template <int G, int VPL, typename T>
+template <int G, int VPL, typename T, bool UNIFORM>
 __global__ void __launch_bounds__(kListThreads) aggregate_views_list_kernel(const __grid_constant__ ListParams p) {
     using V16 = Vec16<T>;
     constexpr int E = V16::kElems;
@@ -65,6 +69,7 @@ __global__ void __launch_bounds__(kListThreads) aggregate_views_list_kernel(cons
     __syncthreads();
 
     const int grp = lane / G, lig = lane % G;
+    const unsigned char *view0 = (p.V > 0) ? sView[0] : nullptr;
     const int c0 = chunk * (kChunkBytes / (int)sizeof(T)) + lig * E;   // first channel of this lane (+ q*G*E)
     const int nxy = p.g.nx * p.g.ny;
     const float inv_nxy = 1.0f / (float)nxy, inv_ny = 1.0f / (float)p.g.ny;
@@ -103,7 +108,8 @@ __global__ void __launch_bounds__(kListThreads) aggregate_views_list_kernel(cons
             float rx, ry;
             rounded_pixel(cx, cy, cz, rx, ry);
             if (active && in_frustum(rx, ry, cz, p.H, p.W))
-                lst[cnt++] = ((uint32_t)v << 20) | ((uint32_t)(int)ry << 10) | (uint32_t)(int)rx;
+                lst[cnt++] = UNIFORM ? ((uint32_t)v * p.view_stride16 + (uint32_t)(int)ry * p.stride_y16 + (uint32_t)(int)rx * p.stride_x16)
+                                     : (((uint32_t)v << 20) | ((uint32_t)(int)ry << 10) | (uint32_t)(int)rx);
         }
         __syncwarp();
 
@@ -139,8 +145,10 @@ __global__ void __launch_bounds__(kListThreads) aggregate_views_list_kernel(cons
                 for (int uu = 0; uu < kListUnroll; ++uu) {
                     if (k + uu < n) {
                         const uint32_t e = jl[k + uu];
-                        const unsigned char *src = sView[e >> 20] + (int64_t)((e >> 10) & 1023u) * p.stride_y_bytes +
-                                                   (int64_t)(e & 1023u) * p.stride_x_bytes + lig * 16;
+                        const unsigned char *src =
+                            UNIFORM ? (view0 + (int64_t)e * 16 + lig * 16)
+                                    : (sView[e >> 20] + (int64_t)((e >> 10) & 1023u) * p.stride_y_bytes +
+                                       (int64_t)(e & 1023u) * p.stride_x_bytes + lig * 16);
 #pragma unroll
                         for (int q = 0; q < VPL; ++q) val[uu][q] = V16::load(reinterpret_cast<const T *>(src + q * G * 16));
                     }
@@ -189,11 +197,11 @@ __global__ void __launch_bounds__(kListThreads) aggregate_views_list_kernel(cons
 
 // ---- launch -----------------------------------------------------------------------------------------------------
 
-template <int G, int VPL, typename T>
+template <int G, int VPL, typename T, bool UNIFORM>
 static cudaError_t launch_list(const ListParams &p, int chunks, cudaStream_t stream) {
     const size_t smem = sizeof(float) * 12 * p.V + sizeof(void *) * p.V +
                         sizeof(uint32_t) * (size_t)(kListThreads / kWarp) * p.nb * p.lcap;
-    auto kernel = aggregate_views_list_kernel<G, VPL, T>;
+    auto kernel = aggregate_views_list_kernel<G, VPL, T, UNIFORM>;
     struct Cached { int dev = -1; size_t smem = 0; int ctas = 0; };
     static thread_local Cached cache;
     int dev = 0;
@@ -221,7 +229,8 @@ static cudaError_t launch_list(const ListParams &p, int chunks, cudaStream_t str
 template <typename T>
 static cudaError_t launch_list_gv(const ListParams &p, int g, int vpl, int chunks, cudaStream_t stream) {
 #define CNRMA_LIST_CASE(GG, VV) \
-    if (g == GG && vpl == VV) return launch_list<GG, VV, T>(p, chunks, stream);
+    if (g == GG && vpl == VV)  \
+        return p.uniform ? launch_list<GG, VV, T, true>(p, chunks, stream) : launch_list<GG, VV, T, false>(p, chunks, stream);
     CNRMA_LIST_CASE(1, 1) CNRMA_LIST_CASE(2, 1) CNRMA_LIST_CASE(4, 1) CNRMA_LIST_CASE(8, 1) CNRMA_LIST_CASE(16, 1)
     CNRMA_LIST_CASE(32, 1) CNRMA_LIST_CASE(32, 2) CNRMA_LIST_CASE(1, 3) CNRMA_LIST_CASE(2, 3) CNRMA_LIST_CASE(4, 3)
     CNRMA_LIST_CASE(8, 3) CNRMA_LIST_CASE(16, 3) CNRMA_LIST_CASE(32, 3) CNRMA_LIST_CASE(32, 4)
@@ -266,6 +275,22 @@ cudaError_t run_aggregate_list(const GridDev &g, const cnrma_features &f, int v0
     if (nb < 32 / G) nb = 32 / G;                         // at least one full gather round
     p.nb = nb;
     for (int i = 0; i < nv; ++i) p.views[i] = f.view_ptrs_host[v0 + i];
+    // equally spaced views (one [V,...] tensor): entries become 32-bit offsets in 16-byte units
+    p.uniform = 0;
+    p.view_stride16 = p.stride_y16 = p.stride_x16 = 0;
+    if (nv > 0 && p.stride_y_bytes % 16 == 0 && p.stride_x_bytes % 16 == 0) {
+        const intptr_t base = reinterpret_cast<intptr_t>(p.views[0]);
+        const intptr_t step = nv > 1 ? reinterpret_cast<intptr_t>(p.views[1]) - base : 0;
+        bool ok = step >= 0 && step % 16 == 0;
+        for (int i = 2; i < nv && ok; ++i) ok = reinterpret_cast<intptr_t>(p.views[i]) - base == (intptr_t)i * step;
+        const int64_t span = (int64_t)(nv - 1) * step + (int64_t)f.height * p.stride_y_bytes + (int64_t)f.width * p.stride_x_bytes;
+        if (ok && span / 16 < ((int64_t)1 << 32)) {
+            p.uniform = 1;
+            p.view_stride16 = (uint32_t)(step / 16);
+            p.stride_y16 = (uint32_t)(p.stride_y_bytes / 16);
+            p.stride_x16 = (uint32_t)(p.stride_x_bytes / 16);
+        }
+    }
     auto launch = [&](const ListParams &lp, int nchunks) -> cudaError_t {
         return (f.dtype == CNRMA_BF16) ? launch_list_gv<__nv_bfloat16>(lp, G, vpl, nchunks, stream)
                                        : launch_list_gv<float>(lp, G, vpl, nchunks, stream);

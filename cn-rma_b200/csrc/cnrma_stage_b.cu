@@ -28,7 +28,7 @@ int rma_record_capacity(int grids, int mode, float threshold, int depth_points) 
 }
 
 RmaWorkspace rma_workspace(int views, int height, int width, int grids, int mode, float threshold, int depth_points,
-                           int64_t bricks, int64_t nvox) {
+                           int64_t nvox) {
     RmaWorkspace w;
     w.rays = (int64_t)views * height * width;
     w.blocks = (w.rays + kRayThreads - 1) / kRayThreads;
@@ -40,8 +40,7 @@ RmaWorkspace rma_workspace(int views, int height, int width, int grids, int mode
     w.off_blk_off = o;  o = align256(o + sizeof(int64_t) * (size_t)w.blocks);
     w.off_rec_w = o;    o = align256(o + sizeof(float) * (size_t)w.rays * (size_t)w.cap);
     w.off_rec_i = o;    o = align256(o + sizeof(float) * (size_t)w.rays * (size_t)w.cap);
-    (void)bricks;
-    w.off_bricks = o;   o = align256(o + 2 * (size_t)nvox);   // two uint8 distance fields (ping-pong)
+    w.off_dist = o;     o = align256(o + 2 * (size_t)nvox);   // two uint8 distance fields (ping-pong)
     w.off_sigmoid = o;  o = align256(o + sizeof(float) * (size_t)nvox);
     w.total = o;
     return w;
@@ -746,7 +745,7 @@ cudaError_t run_march(const GridDev &g, const float *pinv, int V, int H, int W, 
         tsdf_sigmoid_kernel<<<vb, 256, 0, stream>>>(tsdf, nvox, sig);
         p.sig = sig;
         if (thr > 0.0f) {
-            uint8_t *d0 = reinterpret_cast<uint8_t *>(base + ws.off_bricks);
+            uint8_t *d0 = reinterpret_cast<uint8_t *>(base + ws.off_dist);
             uint8_t *d1 = d0 + nvox;
             dist_boundary_kernel<<<vb, 256, 0, stream>>>(g, sig, d0);
             dist_pass_kernel<<<vb, 256, 0, stream>>>(g, 2, d0, d1);
@@ -869,11 +868,4 @@ cudaError_t run_expand(int64_t rays, int N, const void *workspace, const RmaWork
     return cudaGetLastError();
 }
 
-}  // namespace cnrma
-
-namespace cnrma {
-int64_t rma_brick_count(const GridDev &g) {
-    (void)g;
-    return 0;   // the brick table was replaced by the per-voxel distance field (sized by nvox)
-}
 }  // namespace cnrma

@@ -45,10 +45,10 @@ CONFIGS = {
                  tsdf="room", grids=40, dtype="f32"),
     "small": dict(views=6, channels=16, height=30, width=40, voxel_dim=(20, 20, 8), voxel_size=0.25,
                   tsdf="room", grids=100, dtype="f32"),
-    # grid sizes that are not multiples of the march's 4^3 bricks
+    # odd grid sizes (border handling of the march's distance field and of partially filled warps)
     "odd": dict(views=4, channels=8, height=20, width=28, voxel_dim=(13, 10, 7), voxel_size=0.3,
                 tsdf="room", grids=120, dtype="f32"),
-    # a room with long runs of uniform bricks (exercises the chained brick skipping), full-length march
+    # a room with large regions of constant TSDF (exercises the march's empty-space jumps), full-length march
     "room40": dict(views=4, channels=8, height=30, width=40, voxel_dim=(40, 40, 16), voxel_size=0.16,
                    tsdf="room", grids=300, dtype="f32"),
 }

@@ -7,7 +7,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import cnrma_b200 as cn
 
-sc = cn.synthetic.make_scene("cfg2", seed=0, with_features=False)
+sc = cn.synthetic.make_scene(sys.argv[1] if len(sys.argv) > 1 else "cfg2", seed=0, with_features=False)
 dev = torch.device("cuda")
 feats = cn.synthetic.device_features(sc, dev, channels_last=True).requires_grad_(True)
 proj = torch.from_numpy(sc.projections).to(dev).unsqueeze(1)

@@ -408,3 +408,22 @@ def test_degenerate_cameras_do_not_crash(cn):
     p[1, 0, 2, 3] = float("nan")
     _px, _py, valid = cn.project_views(p, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride, sc.height, sc.width)
     assert not bool(valid[1].any())
+
+
+def test_views_in_separate_allocations(cn, scene):
+    """Per-view tensors that do not sit at equal strides in one allocation (pointer-table path of both Stage A
+    kernels and of the fill kernel) give the same bits as the stacked tensor."""
+    sc = scene
+    p, f, t = _scene_tensors(sc)
+    pad = []
+    views = [None] * sc.views
+    for v in reversed(range(sc.views)):            # allocated in reverse order, with gaps of varying size between them
+        pad.append(torch.empty(1024 * (v + 1), device="cuda"))
+        views[v] = f[v].clone(memory_format=torch.preserve_format)
+    a = cn.aggregate_views(p, f, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
+    b = cn.aggregate_views(p, views, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
+    assert torch.equal(a[1], b[1])
+    assert torch.equal(a[0].contiguous().view(torch.int32), b[0].contiguous().view(torch.int32))
+    ra = cn.rma_points(p, f, t, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride, grids=sc.grids, threshold=0.05)[0]
+    rb = cn.rma_points(p, views, t, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride, grids=sc.grids, threshold=0.05)[0]
+    assert torch.equal(ra, rb)
