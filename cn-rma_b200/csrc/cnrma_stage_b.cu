@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(kRayThreads) fill_rows_kernel(const __grid_con
 // cp.async.bulk.global.shared) and writes the few unaligned floats at either end itself: ~6.3 TB/s.
 constexpr int kStageBytes = 8192;   // per-warp staging buffer; 3 CTAs x 8 warps x 8 KB = 192 KB per SM
 
-template <typename T>
+template <typename T, int NJ>   // NJ = ceil(C / 32) register groups per lane (1, 2, 4 or 8)
 __global__ void __launch_bounds__(kRayThreads) fill_rows_tma_kernel(const __grid_constant__ FillParams p) {
     extern __shared__ __align__(128) unsigned char stage_raw[];
     __shared__ int s_warp_rows[kRayThreads / kWarp];
@@ -613,9 +613,9 @@ __global__ void __launch_bounds__(kRayThreads) fill_rows_tma_kernel(const __grid
         float o[3], d[3];
         ray_of_pixel(p.pinv + 16 * view, u, v, o, d);
         const T *feat = static_cast<const T *>(p.views[view - p.view_base]) + (int64_t)v * p.stride_y + (int64_t)u * p.stride_x;
-        float f[kFillRegs];
+        float f[NJ];
 #pragma unroll
-        for (int j = 0; j < kFillRegs; ++j) {
+        for (int j = 0; j < NJ; ++j) {
             const int c = j * 32 + lane;
             f[j] = (c < p.C) ? load_feat<T>(feat + c) : 0.0f;
         }
@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(kRayThreads) fill_rows_tma_kernel(const __grid
                     const float wn = __shfl_sync(0xffffffffu, wk, kb + k);
                     float *row = stage + hw4 + k * cols + col0;
 #pragma unroll
-                    for (int j = 0; j < kFillRegs; ++j) {
+                    for (int j = 0; j < NJ; ++j) {
                         const int c = j * 32 + lane;
                         if (c < p.C) row[c] = p.normalize ? __fmul_rn(f[j], wn) : f[j];
                     }
@@ -795,21 +795,27 @@ static cudaError_t launch_fill(FillParams &p, int dtype, const void *const *view
                          reinterpret_cast<uintptr_t>(p.rows) % 4 == 0;
         if (tma) {
             const size_t smem = (size_t)(kRayThreads / kWarp) * kStageBytes;
-            static thread_local int attr_dev[2] = {-1, -1};   // dynamic-smem opt-in done once per device
+            static thread_local int attr_dev[8] = {-1, -1, -1, -1, -1, -1, -1, -1};   // dynamic-smem opt-in, once per device
             int dev = 0;
             cudaGetDevice(&dev);
+            const int nj = (p.C + 31) / 32;
+            auto go = [&](auto kernel, int slot) {
+                if (attr_dev[slot] != dev) {
+                    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    attr_dev[slot] = dev;
+                }
+                kernel<<<blocks, kRayThreads, smem, stream>>>(p);
+            };
             if (dtype == CNRMA_BF16) {
-                if (attr_dev[1] != dev) {
-                    cudaFuncSetAttribute(fill_rows_tma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    attr_dev[1] = dev;
-                }
-                fill_rows_tma_kernel<__nv_bfloat16><<<blocks, kRayThreads, smem, stream>>>(p);
+                if (nj <= 1) go(fill_rows_tma_kernel<__nv_bfloat16, 1>, 0);
+                else if (nj <= 2) go(fill_rows_tma_kernel<__nv_bfloat16, 2>, 1);
+                else if (nj <= 4) go(fill_rows_tma_kernel<__nv_bfloat16, 4>, 2);
+                else go(fill_rows_tma_kernel<__nv_bfloat16, 8>, 3);
             } else {
-                if (attr_dev[0] != dev) {
-                    cudaFuncSetAttribute(fill_rows_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    attr_dev[0] = dev;
-                }
-                fill_rows_tma_kernel<float><<<blocks, kRayThreads, smem, stream>>>(p);
+                if (nj <= 1) go(fill_rows_tma_kernel<float, 1>, 4);
+                else if (nj <= 2) go(fill_rows_tma_kernel<float, 2>, 5);
+                else if (nj <= 4) go(fill_rows_tma_kernel<float, 4>, 6);
+                else go(fill_rows_tma_kernel<float, 8>, 7);
             }
         } else if (dtype == CNRMA_BF16) {
             fill_rows_kernel<__nv_bfloat16, SCATTER><<<blocks, kRayThreads, 0, stream>>>(p);
