@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libcnrma_b200.so")
 SOURCES = ["cnrma_abi.cu", "cnrma_stage_a.cu", "cnrma_stage_a_list.cu", "cnrma_stage_b.cu", "cnrma_backward.cu",
-           "cnrma_handoff.cu"]
+           "cnrma_handoff.cu", "cnrma_fusion.cu"]
 HEADERS = ["cnrma_common.cuh", "cnrma_internal.cuh", os.path.join("..", "..", "include", "cnrma_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -107,6 +107,9 @@ _SIGNATURES = {
     "cnrma_rma_fill_selected": (C.c_int, [C.POINTER(Grid), C.c_void_p, C.POINTER(Features), C.c_int, C.c_float, C.c_int,
                                           C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "cnrma_tsdf_integrate": (C.c_int, [C.POINTER(Grid), C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_void_p),
+                                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_float,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cnrma_rma_expand": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
 }

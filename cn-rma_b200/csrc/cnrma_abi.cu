@@ -306,6 +306,23 @@ int cnrma_rma_fill_backward(const cnrma_grid *grid, const cnrma_features *grad_f
     return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
 }
 
+int cnrma_tsdf_integrate(const cnrma_grid *grid, const float *projections, int64_t proj_frame_stride, int frames,
+                         const float *const *depth_ptrs_host, const float *const *color_ptrs_host,
+                         const int64_t *const *label_ptrs_host, int height, int width, float trunc_margin, float *tsdf,
+                         float *weight, float *color, int64_t *label, void *stream) {
+    if (!grid_ok(grid) || !projections || !depth_ptrs_host || !tsdf || !weight || frames <= 0 || height <= 0 ||
+        width <= 0 || !(trunc_margin > 0.0f))
+        return CNRMA_ERR_ARG;
+    for (int f = 0; f < frames; ++f)
+        if (!depth_ptrs_host[f]) return CNRMA_ERR_ARG;
+    const int d = device_ok();
+    if (d != CNRMA_OK) return d;
+    const cudaError_t e = run_tsdf_integrate(to_dev(*grid), projections, proj_frame_stride, frames, depth_ptrs_host,
+                                             color_ptrs_host, label_ptrs_host, height, width, trunc_margin, tsdf, weight,
+                                             color, label, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
+}
+
 int cnrma_rma_expand(int views, int height, int width, int grids, float threshold, const void *workspace,
                      float *weights, uint8_t *keep, void *stream) {
     if (!workspace || views <= 0 || height <= 0 || width <= 0 || grids <= 0) return CNRMA_ERR_ARG;

@@ -49,6 +49,12 @@ cudaError_t run_select_rows(const float *rows, int64_t row_stride, int cols, int
                             const int32_t *prefix, const float *offset3_host, float *out, int64_t out_stride,
                             int64_t capacity, cudaStream_t stream);
 
+// cnrma_fusion.cu
+cudaError_t run_tsdf_integrate(const GridDev &g, const float *proj, int64_t proj_stride, int frames,
+                               const float *const *depth_host, const float *const *color_host,
+                               const int64_t *const *label_host, int H, int W, float trunc_margin, float *tsdf,
+                               float *weight, float *color, int64_t *label, cudaStream_t stream);
+
 // cnrma_backward.cu
 cudaError_t run_aggregate_views_backward(const GridDev &g, const cnrma_features &gf, const float *proj,
                                          int64_t proj_stride, float stride, uint32_t flags, const float *grad_volume,

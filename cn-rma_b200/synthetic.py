@@ -90,12 +90,12 @@ class Scene:
         return self.views * self.height * self.width * self.grids
 
 
-def ring_cameras(views, height, width, stride, extent, rng):
+def ring_cameras(views, height, width, stride, extent, rng, return_poses=False):
     """Pinhole cameras on a ring inside the room, looking across it.
 
     fx = fy = 0.9 * W_img (ScanNet's 577/640), principal point at the image
     centre, W_img = stride * W.  Returns projections [V,3,4] float32 =
-    K @ inv(E)[:3] evaluated in float64 and rounded once.
+    K @ inv(E)[:3] evaluated in float64 and rounded once (and, on request, K and the poses E).
     """
     w_img, h_img = stride * width, stride * height
     k = np.array([[0.9 * w_img, 0.0, 0.5 * w_img],
@@ -105,6 +105,7 @@ def ring_cameras(views, height, width, stride, extent, rng):
     centre = np.array([0.5 * ex, 0.5 * ey, 0.45 * ez])
     radius = 0.22 * min(ex, ey)
     out = np.empty((views, 3, 4), dtype=np.float32)
+    poses = np.empty((views, 4, 4), dtype=np.float64)
     for i in range(views):
         ang = 2.0 * math.pi * (i + 0.25 * rng.random()) / views
         cam = centre + np.array([radius * math.cos(ang), radius * math.sin(ang), 0.1 * ez * (rng.random() - 0.5)])
@@ -117,7 +118,29 @@ def ring_cameras(views, height, width, stride, extent, rng):
         down = np.cross(fwd, right)
         pose = np.eye(4)
         pose[:3, 0], pose[:3, 1], pose[:3, 2], pose[:3, 3] = right, down, fwd, cam
+        poses[i] = pose
         out[i] = (k @ np.linalg.inv(pose)[:3, :]).astype(np.float32)
+    return (out, k, poses) if return_poses else out
+
+
+def room_depth_maps(k, poses, height, width, extent, rng=None, holes=0.02):
+    """Depth maps [V,H,W] (metres along the optical axis, float32) of the box room whose walls sit at 15 % / 85 % of
+    the extent, seen from cameras inside it; a fraction `holes` of the pixels is set to 0 (no depth reading), the
+    value the fusion code treats as invalid (data_prepare/scannet/tsdf.py:422-423)."""
+    lo = np.array([0.15 * e for e in extent])
+    hi = np.array([0.85 * e for e in extent])
+    u, v = np.meshgrid(np.arange(width), np.arange(height))
+    rays_cam = np.stack([(u - k[0, 2]) / k[0, 0], (v - k[1, 2]) / k[1, 1], np.ones_like(u, dtype=np.float64)], axis=-1)
+    out = np.empty((len(poses), height, width), dtype=np.float32)
+    for i, pose in enumerate(poses):
+        d = rays_cam @ pose[:3, :3].T                      # world directions, z_cam = 1 per unit of t
+        c = pose[:3, 3]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t = np.where(d > 0, (hi - c) / d, np.where(d < 0, (lo - c) / d, np.inf))
+        depth = t.min(axis=-1)
+        if rng is not None and holes > 0:
+            depth = np.where(rng.random(depth.shape) < holes, 0.0, depth)
+        out[i] = depth.astype(np.float32)
     return out
 
 

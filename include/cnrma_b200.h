@@ -228,6 +228,22 @@ int cnrma_rma_fill_selected(const cnrma_grid *grid, const float *pinv, const cnr
                             const int32_t *prefix, const float *offset_host, float *rows, int64_t row_stride,
                             int64_t capacity, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * GT TSDF fusion (offline data preparation): TSDFFusion.integrate, data_prepare/scannet/tsdf.py:402-451 (same code in
+ * data_prepare/arkit/tsdf.py), for a batch of frames in one pass over the volume; frames are applied in order, so
+ * the volumes are bit-identical to calling the reference once per frame.
+ *   projections   [frames] 3x4 row-major (full resolution: no stride scaling), element stride proj_frame_stride
+ *   depth / color / label pointer tables: HOST arrays of DEVICE pointers: depth f32 [H,W] (0 = no reading),
+ *                 color f32 [3,H,W] (table or entries may be NULL), label i64 [H,W] (table or entries may be NULL)
+ *   trunc_margin  voxel_size * trunc_ratio (tsdf.py:373)
+ *   tsdf, weight  f32 [nvox] state (tsdf starts at 1, weight at 0: tsdf.py:379-380); color f32 [3,nvox] or NULL;
+ *                 label i64 [nvox] or NULL (starts at -1)
+ * ------------------------------------------------------------------------------------------- */
+int cnrma_tsdf_integrate(const cnrma_grid *grid, const float *projections, int64_t proj_frame_stride, int frames,
+                         const float *const *depth_ptrs_host, const float *const *color_ptrs_host,
+                         const int64_t *const *label_ptrs_host, int height, int width, float trunc_margin, float *tsdf,
+                         float *weight, float *color, int64_t *label, void *stream);
+
 /* Dense per-sample view of the march records for parity tests: weights f32 [V*H*W*N] (0 where not kept,
  * i.e. rm.py:767 `weights * valid_final`) and keep uint8 [V*H*W*N].  NEUS mode only. */
 int cnrma_rma_expand(int views, int height, int width, int grids, float threshold, const void *workspace,

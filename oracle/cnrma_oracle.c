@@ -447,3 +447,55 @@ ORACLE_API void cnrma_oracle_scatter_rows(int64_t M, int C, const float *rows, c
         for (int c = 0; c < C; ++c) wsum[(size_t)c * nvox + vox] += (double)r[3] * (double)r[4 + c];
     }
 }
+
+/* GT TSDF fusion, one depth frame: data_prepare/scannet/tsdf.py:402-451
+ * TSDFFusion.integrate, restated per voxel ("fz.py" below = that file).
+ *   fz.py:413-416  camera = P @ [world;1]; px, py = round(x/z), round(y/z); pz = z     (same idiom as rm.py:51-54)
+ *   fz.py:419-423  valid = frustum & depth[py,px] > 0
+ *   fz.py:426-427  dist = clamp((pz - depth) / trunc_margin, min=-1)
+ *   fz.py:430-433  valid &= dist < 1
+ *   fz.py:436-437  weight == 0: tsdf = dist
+ *   fz.py:440-445  near = dist > -1; weight != 0 & near: tsdf += dist; near: weight += 1
+ *   fz.py:447-450  near: color += color_img[:, py, px]; label = label_img[py, px]
+ * P is the frame's 3x4 projection (full resolution, not stride-scaled). color / label images and volumes may be NULL. */
+ORACLE_API void cnrma_oracle_tsdf_integrate(int nx, int ny, int nz, float voxel_size, const float *origin,
+                                            const float *P, int H, int W, const float *depth, const float *color_img,
+                                            const int64_t *label_img, float trunc_margin, float *tsdf, float *weight,
+                                            float *color, int64_t *label) {
+    size_t nvox = (size_t)nx * ny * nz;
+    size_t plane = (size_t)H * W;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int x = 0; x < nx; ++x)
+        for (int y = 0; y < ny; ++y)
+            for (int z = 0; z < nz; ++z) {
+                size_t i = ((size_t)x * ny + y) * nz + z;
+                float wx = (float)x * voxel_size + origin[0];
+                float wy = (float)y * voxel_size + origin[1];
+                float wz = (float)z * voxel_size + origin[2];
+                float cam[3];
+                for (int r = 0; r < 3; ++r) {
+                    float acc = P[4 * r + 0] * wx;
+                    acc = fmaf(P[4 * r + 1], wy, acc);
+                    acc = fmaf(P[4 * r + 2], wz, acc);
+                    acc = fmaf(P[4 * r + 3], 1.0f, acc);
+                    cam[r] = acc;
+                }
+                int64_t px = f2l(rintf(cam[0] / cam[2]));
+                int64_t py = f2l(rintf(cam[1] / cam[2]));
+                if (!((px >= 0) & (py >= 0) & (px < W) & (py < H) & (cam[2] > 0.0f))) continue;
+                float d = depth[(size_t)py * W + (size_t)px];
+                if (!(d > 0.0f)) continue;
+                float dist = (cam[2] - d) / trunc_margin;
+                if (dist < -1.0f) dist = -1.0f;          /* clamp(min=-1) */
+                if (!(dist < 1.0f)) continue;
+                int first = (weight[i] == 0.0f);
+                if (first) tsdf[i] = dist;
+                if (dist > -1.0f) {
+                    if (!first) tsdf[i] = tsdf[i] + dist;
+                    weight[i] = weight[i] + 1.0f;
+                    if (color && color_img)
+                        for (int c = 0; c < 3; ++c) color[(size_t)c * nvox + i] += color_img[(size_t)c * plane + (size_t)py * W + (size_t)px];
+                    if (label && label_img) label[i] = label_img[(size_t)py * W + (size_t)px];
+                }
+            }
+}

@@ -223,3 +223,21 @@ def dense_rma(rows, voxel_dim, voxel_size, origin):
     lib().cnrma_oracle_scatter_rows(C.c_int64(m), C.c_int(c), _p(rows), _p(o), C.c_float(voxel_size), C.c_int(x),
                                     C.c_int(y), C.c_int(z), _p(wsum), _p(wtot))
     return wsum.astype(np.float32).reshape(c, x, y, z), wtot.astype(np.float32).reshape(x, y, z)
+
+
+def tsdf_integrate(voxel_dim, voxel_size, origin, projection, depth, trunc_margin, tsdf, weight, color_img=None,
+                   color=None, label_img=None, label=None):
+    """One frame of TSDFFusion.integrate (data_prepare/scannet/tsdf.py:402-451), in place on the numpy volumes
+    tsdf / weight [nvox] f32 (and color [3,nvox] f32, label [nvox] i64 when given)."""
+    nx, ny, nz = voxel_dim
+    h, w = depth.shape
+    keep = (_f(origin).reshape(3), _f(projection).reshape(12), _f(depth),
+            None if color_img is None else _f(color_img),
+            None if label_img is None else np.ascontiguousarray(label_img, dtype=np.int64))
+    assert tsdf.dtype == np.float32 and weight.dtype == np.float32 and tsdf.flags.c_contiguous
+    lib().cnrma_oracle_tsdf_integrate(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_float(voxel_size), _p(keep[0]),
+                                      _p(keep[1]), C.c_int(h), C.c_int(w), _p(keep[2]),
+                                      None if keep[3] is None else _p(keep[3]),
+                                      None if keep[4] is None else _p(keep[4]), C.c_float(trunc_margin),
+                                      _p(tsdf), _p(weight), None if color is None else _p(color),
+                                      None if label is None else _p(label))
