@@ -42,6 +42,32 @@ def parse_args():
     return ap.parse_args()
 
 
+def bind_to_gpu_numa_node(torch, index):
+    """Pins this rank to the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI device) so that the pinned
+    host buffers of the end-to-end leg are first-touched on the GPU's own NUMA node; without it every rank's copies
+    cross the socket interconnect and the N-GPU end-to-end number is capped by it.  Best effort: returns the CPU
+    list used, or None."""
+    try:
+        props = torch.cuda.get_device_properties(index)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return spec
+    except (OSError, AttributeError, ValueError):
+        pass
+    return None
+
+
 def load_traffic(config):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the main kernels from the committed
     `ncu --set full` capture of this same command (profiles/traffic.json); {} if the config was not profiled."""
@@ -217,6 +243,7 @@ def main():
                          "(use --impl reference for the CPU oracle arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cn.load()
@@ -346,7 +373,8 @@ def main():
         "vs_baseline": None, "dtype": "f32" if esz == 4 else "bf16", "data": "synthetic",
         "config": {"workload": workload_name(args.config, sc), "layout": "channels-last feature maps (NHWC physical)",
                    "l2": "inputs (%.0f MB features/scene) exceed the 126 MB L2; no explicit flush" % (V * H * W * C * esz / 1e6),
-                   "parallelism": f"scene-dp{world}", "rows_per_scene": m_rows, "threshold": thr},
+                   "parallelism": f"scene-dp{world}", "rows_per_scene": m_rows, "threshold": thr,
+                   "host_cpus": numa},
         "scenes_per_s": world / (ms_step * 1e-3),
         "ray_steps_per_s": world * sc.ray_steps / (ms_step * 1e-3),
         "stage_ms": {"stage_a": ms_a, "march": ms_march, "fill": ms_fill},
