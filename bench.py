@@ -363,6 +363,27 @@ def main():
             dist.destroy_process_group()
         return
 
+    # --- the lift as the detector consumes it (reported beside the headline, not part of it): Stage B fused with the
+    # point-cloud hand-off (rm.py:339-407, max_points = 500000 as in the shipped config), mask drawn on the device
+    handoff = None
+    if args.stage == "both" and world == 1:
+        def lift_and_handoff():
+            n_rows = m_rows
+            mask = cn.sample_points_device(n_rows, 500000, 1234, dev)
+            return cn.rma_points_selected(proj_host, feats, tsdf, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride,
+                                          offsets=[[0.0, 0.0, 0.0]], masks=[mask], grids=sc.grids, threshold=thr)
+        for _ in range(3):
+            lift_and_handoff()
+        torch.cuda.synchronize()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        for _ in range(10):
+            sel = lift_and_handoff()
+        h1.record()
+        torch.cuda.synchronize()
+        handoff = {"ms_per_scene": h0.elapsed_time(h1) / 10, "rows_kept": int(sel[0][0].shape[0]), "rows_total": m_rows,
+                   "what": "sample mask (device) + march + fill of the kept rows only, offset added; excludes Stage A"}
+
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         cpu_baseline = run_cpu_baseline(args, sc)
@@ -379,6 +400,7 @@ def main():
         "ray_steps_per_s": world * sc.ray_steps / (ms_step * 1e-3),
         "stage_ms": {"stage_a": ms_a, "march": ms_march, "fill": ms_fill},
         "kernels": kernels, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
+        "handoff": handoff,
         # aggregate_views | tsdf_sigmoid, dist_boundary, 3 x dist_pass, march_neus, scan_blocks | fill_rows_tma
         "gpu_launches": (9 if args.stage == "both" else (1 if args.stage == "a" else 8)) * args.steps,
     }

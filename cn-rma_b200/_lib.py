@@ -107,6 +107,8 @@ _SIGNATURES = {
     "cnrma_rma_fill_selected": (C.c_int, [C.POINTER(Grid), C.c_void_p, C.POINTER(Features), C.c_int, C.c_float, C.c_int,
                                           C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "cnrma_sample_workspace_bytes": (C.c_int, [C.POINTER(C.c_size_t)]),
+    "cnrma_sample_mask": (C.c_int, [C.c_int64, C.c_int64, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "cnrma_tsdf_integrate": (C.c_int, [C.POINTER(Grid), C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_void_p),
                                        C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_float,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -306,6 +306,24 @@ int cnrma_rma_fill_backward(const cnrma_grid *grid, const cnrma_features *grad_f
     return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
 }
 
+int cnrma_sample_workspace_bytes(size_t *bytes) {
+    if (!bytes) return CNRMA_ERR_ARG;
+    *bytes = sample_workspace_bytes();
+    return CNRMA_OK;
+}
+
+int cnrma_sample_mask(int64_t rows, int64_t keep, uint64_t seed, void *workspace, size_t workspace_bytes, uint8_t *mask,
+                      void *stream) {
+    if (!workspace || !mask || rows < 0 || keep < 0) return CNRMA_ERR_ARG;
+    if (rows >= ((int64_t)1 << 27)) return CNRMA_ERR_UNSUPPORTED;   // the boundary bin (rows / 65536 keys on average) must fit its 8192-key buffer
+    if (workspace_bytes < sample_workspace_bytes()) return CNRMA_ERR_CAPACITY;
+    if (reinterpret_cast<uintptr_t>(workspace) % 8 != 0) return CNRMA_ERR_LAYOUT;
+    const int d = device_ok();
+    if (d != CNRMA_OK) return d;
+    const cudaError_t e = run_sample_mask(rows, keep, seed, workspace, mask, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
+}
+
 int cnrma_tsdf_integrate(const cnrma_grid *grid, const float *projections, int64_t proj_frame_stride, int frames,
                          const float *const *depth_ptrs_host, const float *const *color_ptrs_host,
                          const int64_t *const *label_ptrs_host, int height, int width, float trunc_margin, float *tsdf,

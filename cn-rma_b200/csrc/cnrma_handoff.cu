@@ -135,3 +135,120 @@ cudaError_t run_select_rows(const float *rows, int64_t row_stride, int cols, int
 }
 
 }  // namespace cnrma
+
+// ---- device-side sampler ---------------------------------------------------------------------------------------------
+// sample_points draws its mask with np.random.choice(N, max_points, replace=False) on the host
+// (fcaf3d_transforms.py:290): a full permutation of ~6 M indices, ~0.2 s per scene -- two orders of magnitude more
+// than the whole lift.  This is the on-device equivalent in distribution (NOT the same random stream, so it is an
+// option, never the parity path): every row gets the key (hash32(seed, i) << 32 | i), the k smallest keys are kept.
+// Keys are distinct by construction, so exactly k rows are selected; the subset is uniform up to the quality of
+// the hash.  Selection = one 16-bit histogram pass over the keys, a scan of the 65536 bins to find the bin that
+// contains the k-th key, a rank computation inside that bin (a few hundred keys), and a final compare pass.
+namespace cnrma {
+
+constexpr int kSampleBins = 65536;
+constexpr int kSampleCand = 8192;   // capacity for the keys of the boundary bin (n / 65536 on average)
+
+struct SampleState {        // lives in the caller's workspace
+    unsigned int hist[kSampleBins];
+    unsigned long long threshold;   // keys <= threshold are kept
+    unsigned int bin;               // boundary bin
+    unsigned int below;             // keys in the bins before it
+    unsigned int ncand;
+    unsigned int overflow;
+    unsigned long long cand[kSampleCand];
+};
+
+__device__ __forceinline__ unsigned long long sample_key(unsigned long long seed, unsigned int i) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);   // splitmix64 finaliser
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (z & 0xFFFFFFFF00000000ull) | i;
+}
+
+__global__ void __launch_bounds__(256) sample_hist_kernel(unsigned long long seed, unsigned int n, SampleState *st) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&st->hist[sample_key(seed, i) >> 48], 1u);
+}
+
+__global__ void __launch_bounds__(1024) sample_find_bin_kernel(unsigned int k, SampleState *st) {
+    __shared__ unsigned int s[1024];
+    const int t = threadIdx.x;
+    unsigned int sum = 0;
+    for (int b = t * 64; b < t * 64 + 64; ++b) sum += st->hist[b];
+    s[t] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const unsigned int add = (t >= o) ? s[t - o] : 0;
+        __syncthreads();
+        s[t] += add;
+        __syncthreads();
+    }
+    const unsigned int before = s[t] - sum;     // keys in the strips before this one
+    if (k > before && k <= s[t]) {              // the k-th smallest key lives in this strip
+        unsigned int run = before;
+        for (int b = t * 64; b < t * 64 + 64; ++b) {
+            if (k <= run + st->hist[b]) {
+                st->bin = b;
+                st->below = run;
+                break;
+            }
+            run += st->hist[b];
+        }
+    }
+    if (t == 0) {
+        st->ncand = 0;
+        st->overflow = 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) sample_collect_kernel(unsigned long long seed, unsigned int n, SampleState *st) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long key = sample_key(seed, i);
+    if ((unsigned int)(key >> 48) == st->bin) {
+        const unsigned int slot = atomicAdd(&st->ncand, 1u);
+        if (slot < kSampleCand) st->cand[slot] = key;
+        else st->overflow = 1;
+    }
+}
+
+__global__ void __launch_bounds__(1024) sample_threshold_kernel(unsigned int k, SampleState *st) {
+    // the (k - below)-th smallest key of the boundary bin: rank by counting (a few hundred keys)
+    const unsigned int m = min(st->ncand, (unsigned int)kSampleCand);
+    const unsigned int want = k - st->below;    // 1-based rank inside the bin
+    for (unsigned int a = threadIdx.x; a < m; a += blockDim.x) {
+        const unsigned long long key = st->cand[a];
+        unsigned int rank = 1;
+        for (unsigned int b = 0; b < m; ++b) rank += (st->cand[b] < key);
+        if (rank == want) st->threshold = key;
+    }
+}
+
+__global__ void __launch_bounds__(256) sample_mask_kernel(unsigned long long seed, unsigned int n, const SampleState *st,
+                                                          uint8_t *__restrict__ mask) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) mask[i] = (uint8_t)(sample_key(seed, i) <= st->threshold);
+}
+
+size_t sample_workspace_bytes() { return (sizeof(SampleState) + 255) / 256 * 256; }
+
+cudaError_t run_sample_mask(int64_t n, int64_t k, unsigned long long seed, void *workspace, uint8_t *mask,
+                            cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    if (k >= n) return cudaMemsetAsync(mask, 1, (size_t)n, stream);
+    if (k <= 0) return cudaMemsetAsync(mask, 0, (size_t)n, stream);
+    SampleState *st = static_cast<SampleState *>(workspace);
+    cudaError_t err = cudaMemsetAsync(st->hist, 0, sizeof(st->hist), stream);
+    if (err != cudaSuccess) return err;
+    const unsigned int blocks = (unsigned int)((n + 255) / 256);
+    sample_hist_kernel<<<blocks, 256, 0, stream>>>(seed, (unsigned int)n, st);
+    sample_find_bin_kernel<<<1, 1024, 0, stream>>>((unsigned int)k, st);
+    sample_collect_kernel<<<blocks, 256, 0, stream>>>(seed, (unsigned int)n, st);
+    sample_threshold_kernel<<<1, 1024, 0, stream>>>((unsigned int)k, st);
+    sample_mask_kernel<<<blocks, 256, 0, stream>>>(seed, (unsigned int)n, st, mask);
+    return cudaGetLastError();
+}
+
+}  // namespace cnrma

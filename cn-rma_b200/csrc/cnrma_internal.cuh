@@ -49,6 +49,10 @@ cudaError_t run_select_rows(const float *rows, int64_t row_stride, int cols, int
                             const int32_t *prefix, const float *offset3_host, float *out, int64_t out_stride,
                             int64_t capacity, cudaStream_t stream);
 
+size_t sample_workspace_bytes();
+cudaError_t run_sample_mask(int64_t n, int64_t k, unsigned long long seed, void *workspace, uint8_t *mask,
+                            cudaStream_t stream);
+
 // cnrma_fusion.cu
 cudaError_t run_tsdf_integrate(const GridDev &g, const float *proj, int64_t proj_stride, int frames,
                                const float *const *depth_host, const float *const *color_host,

@@ -634,6 +634,22 @@ def sample_points(n, max_points, rng=None):
     return new_mask
 
 
+def sample_points_device(n, max_points, seed, device):
+    """On-device counterpart of sample_points: a bool CUDA tensor [n] with exactly min(n, max_points) ones, a uniform
+    random subset keyed by `seed` (equivalent in distribution to the reference's numpy draw, not the same stream --
+    use sample_points for parity).  Avoids the host-side permutation of n indices (~0.2 s for 6 M points)."""
+    lib = _lib.load()
+    device = torch.device(device)
+    mask = torch.empty(n, dtype=torch.bool, device=device)
+    nbytes = C.c_size_t(0)
+    _lib.check(lib.cnrma_sample_workspace_bytes(C.byref(nbytes)), "cnrma_sample_workspace_bytes")
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        _lib.check(lib.cnrma_sample_mask(n, int(max_points), int(seed) & 0xFFFFFFFFFFFFFFFF, C.c_void_p(ws.data_ptr()),
+                                         nbytes.value, C.c_void_p(mask.data_ptr()), _stream(device)), "cnrma_sample_mask")
+    return mask
+
+
 def _mask_prefix(mask_dev):
     lib = _lib.load()
     device = mask_dev.device

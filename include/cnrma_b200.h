@@ -219,6 +219,13 @@ int cnrma_select_rows(const float *rows, int64_t row_stride, int cols, int64_t n
                       const int32_t *prefix, const float *offset_host, float *out, int64_t out_stride,
                       int64_t capacity, void *stream);
 
+/* On-device alternative to sample_points' numpy draw (an option, never the parity path: it is equivalent in
+ * distribution, not the same random stream): mask[i] = 1 for exactly min(keep, rows) rows chosen uniformly at random
+ * (keyed by `seed`, deterministic), 0 elsewhere.  Removes the ~0.2 s host-side np.random.choice per scene. */
+int cnrma_sample_workspace_bytes(size_t *bytes);
+int cnrma_sample_mask(int64_t rows, int64_t keep, uint64_t seed, void *workspace, size_t workspace_bytes, uint8_t *mask,
+                      void *stream);
+
 /* cnrma_rma_fill fused with the hand-off: only the kept rows are produced (at out row prefix[row], offset added),
  * i.e. aggregate_2d_features_ray_marching + switch_pointcloud in one pass.  mask / prefix index the M rows of the
  * march in their (view, v, u, step) order. */

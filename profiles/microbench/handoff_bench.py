@@ -49,3 +49,10 @@ print(f"rows {full.shape[0]} -> {int(mask.sum())}")
 print(f"rma_points + switch_pointcloud : {timed(two_steps):.3f} ms")
 print(f"fused selected fill            : {timed(fused):.3f} ms")
 print(f"switch_pointcloud alone        : {timed(lambda: cn.switch_pointcloud([full], off, masks=[mask])):.3f} ms")
+
+import time
+t0 = time.perf_counter()
+cn.sample_points(full.shape[0], 500000, np.random.RandomState(1))
+host_ms = (time.perf_counter() - t0) * 1e3
+dev_ms = timed(lambda: cn.sample_points_device(full.shape[0], 500000, 1, dev))
+print(f"mask draw: numpy on the host {host_ms:.1f} ms, on the device {dev_ms:.3f} ms")

@@ -70,3 +70,28 @@ def test_mirror_switch_pointcloud(golden):
     assert boxes == ["boxes"]
     assert np.array_equal(coords[0].cpu().numpy().view(np.uint32), g["handoff_coords"].view(np.uint32))
     assert np.array_equal(feats[0].cpu().numpy().view(np.uint32), g["handoff_features"].view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_device_sampler_properties():
+    """The on-device alternative to sample_points: exact count, deterministic per seed, uniform, usable as a mask."""
+    n, k = 200_000, 30_000
+    m1 = cn.sample_points_device(n, k, seed=7, device="cuda")
+    m2 = cn.sample_points_device(n, k, seed=7, device="cuda")
+    m3 = cn.sample_points_device(n, k, seed=8, device="cuda")
+    assert m1.dtype == torch.bool and int(m1.sum()) == k
+    assert torch.equal(m1, m2) and not torch.equal(m1, m3) and int(m3.sum()) == k
+    # uniformity: counts in 100 equal slices of the index range follow Binomial(2000, 0.15): std ~16
+    per_slice = m1.view(100, -1).sum(1).float()
+    assert abs(float(per_slice.mean()) - k / 100) < 1e-3
+    assert float(per_slice.std()) < 3 * (2000 * 0.15 * 0.85) ** 0.5
+    # overlap of two independent draws ~ k*k/n
+    both = int((m1 & m3).sum())
+    assert abs(both - k * k / n) < 6 * (k * k / n) ** 0.5
+    assert bool(cn.sample_points_device(10, 25, seed=1, device="cuda").all())
+    assert not bool(cn.sample_points_device(10, 0, seed=1, device="cuda").any())
+    for kk in (1, 9, 10):
+        assert int(cn.sample_points_device(10, kk, seed=3, device="cuda").sum()) == min(kk, 10)
+    pts = torch.randn(n, 7, device="cuda")
+    coords, feats = cn.switch_pointcloud([pts], [[0.0, 0.0, 0.0]], masks=[m1])
+    assert torch.equal(torch.cat((coords[0], feats[0]), 1), pts[m1])
