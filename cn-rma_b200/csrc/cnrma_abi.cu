@@ -114,6 +114,21 @@ int cnrma_aggregate_views(const cnrma_grid *grid, const cnrma_features *features
     return CNRMA_OK;
 }
 
+int cnrma_aggregate_views_bilinear(const cnrma_grid *grid, const cnrma_features *features, const float *projections,
+                                   int64_t proj_view_stride, float stride, uint32_t flags, float *volume, int32_t *count,
+                                   uint8_t *valid, void *stream) {
+    if (!grid_ok(grid) || !features || !projections || !volume || !count || !(stride > 0.0f)) return CNRMA_ERR_ARG;
+    if (flags & ~CNRMA_AGG_MEAN) return CNRMA_ERR_ARG;
+    const int fs = features_ok(features, true);
+    if (fs != CNRMA_OK) return fs;
+    if (features->views > kMaxViewsPerLaunch) return CNRMA_ERR_UNSUPPORTED;
+    const int d = device_ok();
+    if (d != CNRMA_OK) return d;
+    const cudaError_t e = run_aggregate_bilinear(to_dev(*grid), *features, projections, proj_view_stride, stride, flags,
+                                                 volume, count, valid, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
+}
+
 int cnrma_selftest_count_division(int max_n, uint64_t *mismatches, void *stream) {
     if (!mismatches || max_n < 1 || max_n > 65535) return CNRMA_ERR_ARG;
     const int d = device_ok();

@@ -288,6 +288,29 @@ def aggregate_views(projections, features, voxel_dim, voxel_size, origin, stride
     return volume, count, valid
 
 
+def aggregate_views_bilinear(projections, features, voxel_dim, voxel_size, origin, stride, mean=True):
+    """OPT-IN extra (not in the reference, which samples nearest): Stage A with bilinear sampling at the projected
+    position, same validity mask / counts as aggregate_views.  Returns (volume, count, valid) in the same layouts."""
+    lib = _lib.load()
+    fs = _FeatureStack(_as_view_list(features), need_vector_layout=True)
+    device = fs.device
+    P = _projections_device(projections, device)
+    nx, ny, nz = (int(v) for v in voxel_dim)
+    grid = _lib.make_grid(voxel_dim, voxel_size, _origin3(origin))
+    buf = torch.empty((fs.B, nx, ny, nz, fs.C), dtype=torch.float32, device=device)
+    count = torch.empty((fs.B, 1, nx, ny, nz), dtype=torch.int32, device=device)
+    valid = torch.empty((fs.B, 1, nx, ny, nz), dtype=torch.bool, device=device)
+    with torch.cuda.device(device):
+        for b in range(fs.B):
+            desc = fs.descriptor(b)
+            _lib.check(lib.cnrma_aggregate_views_bilinear(C.byref(grid), C.byref(desc), C.c_void_p(P[0, b].data_ptr()),
+                                                          fs.B * 12, float(stride), _lib.AGG_MEAN if mean else 0,
+                                                          C.c_void_p(buf[b].data_ptr()), C.c_void_p(count[b].data_ptr()),
+                                                          C.c_void_p(valid[b].data_ptr()), _stream(device)),
+                       "cnrma_aggregate_views_bilinear")
+    return buf.permute(0, 4, 1, 2, 3), count, valid
+
+
 def _check_out(volume, count, B, Cc, nx, ny, nz, count_f32):
     if tuple(volume.shape) != (B, Cc, nx, ny, nz) or volume.dtype != torch.float32 or not volume.is_cuda:
         raise ValueError("out volume has the wrong shape, dtype or device")

@@ -112,6 +112,15 @@ int cnrma_aggregate_views(const cnrma_grid *grid, const cnrma_features *features
                           int64_t vol_stride_voxel, int64_t vol_stride_channel, int32_t *count, uint8_t *valid,
                           void *stream);
 
+/* OPT-IN extra, not a replacement of any reference function: Stage A with bilinear instead of nearest sampling
+ * (BASELINE.json's north_star names a bilinear gather; the reference samples nearest and parity with it wins, so
+ * every other entry point samples nearest).  Same validity mask and view count as cnrma_aggregate_views; value =
+ * grid_sample(bilinear, border, align_corners=True) at (cx/cz, cy/cz), summed in view order (/ count with
+ * CNRMA_AGG_MEAN).  volume f32 [nvox, C] channels-last contiguous; up to 512 views. */
+int cnrma_aggregate_views_bilinear(const cnrma_grid *grid, const cnrma_features *features, const float *projections,
+                                   int64_t proj_view_stride, float stride, uint32_t flags, float *volume, int32_t *count,
+                                   uint8_t *valid, void *stream);
+
 /* Proof obligation of the fused mean (rm.py:251 `volume / valid`): the kernel divides by the view count with
  * one correctly rounded reciprocal and a Markstein correction instead of a generic division.  This entry
  * point checks that shortcut against IEEE division for every count in [1, max_n] and every fp32 significand

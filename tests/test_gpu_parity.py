@@ -427,3 +427,43 @@ def test_views_in_separate_allocations(cn, scene):
     ra = cn.rma_points(p, f, t, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride, grids=sc.grids, threshold=0.05)[0]
     rb = cn.rma_points(p, views, t, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride, grids=sc.grids, threshold=0.05)[0]
     assert torch.equal(ra, rb)
+
+
+def test_bilinear_opt_in_matches_grid_sample(cn, scene):
+    """The opt-in bilinear variant (not in the reference): counts identical to the nearest path, values equal to a
+    plain PyTorch fp32 restatement with grid_sample(bilinear, border, align_corners=True)."""
+    import torch.nn.functional as TF
+    sc = scene
+    for dtype in (None, torch.bfloat16):
+        _check_bilinear(cn, sc, dtype)
+
+
+def _check_bilinear(cn, sc, dtype):
+    import torch.nn.functional as TF
+    p, f, _ = _scene_tensors(sc, dtype=dtype)
+    vol, cnt, valid = cn.aggregate_views_bilinear(p, f, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
+    _v, cnt_nearest, _ = cn.aggregate_views(p, f, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
+    assert torch.equal(cnt, cnt_nearest)
+    nx, ny, nz = sc.voxel_dim
+    g = torch.stack(torch.meshgrid(torch.arange(nx), torch.arange(ny), torch.arange(nz), indexing="ij"), 0).reshape(3, -1)
+    # Positions: torch.mm on the CPU is the same k-ordered FMA chain the kernel uses (see the oracle header), so the
+    # fp32 (cx/cz, cy/cz) below are bit-identical to the kernel's; the sampling itself is then done in float64, which
+    # leaves only the kernel's fp32 weight / accumulation rounding -> 1e-5 of the value range.
+    world = g.float() * sc.voxel_size + torch.from_numpy(sc.origin)[:, None]
+    world = torch.cat((world, torch.ones_like(world[:1])), 0)
+    _px, _py, masks = cn.project_views(p, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride, sc.height, sc.width)
+    acc = torch.zeros((sc.channels, nx * ny * nz), device="cuda", dtype=torch.float64)
+    for v in range(sc.views):
+        P = cn.scale_projections(p[v].cpu(), sc.stride)[0].cpu()
+        cam = torch.mm(P, world)
+        fx, fy = (cam[0] / cam[2]).cuda().double(), (cam[1] / cam[2]).cuda().double()
+        gx = 2 * fx / (sc.width - 1) - 1
+        gy = 2 * fy / (sc.height - 1) - 1
+        grid = torch.stack((gx, gy), -1).view(1, 1, -1, 2)
+        samp = TF.grid_sample(f[v].contiguous().double(), grid, mode="bilinear", padding_mode="border",
+                              align_corners=True)[0, :, 0]
+        m = masks[v, 0].reshape(-1)
+        acc += torch.where(m[None], samp, torch.zeros_like(samp))
+    ref = (acc / cnt.view(1, -1).clamp_min(1).double()).view(sc.channels, nx, ny, nz)
+    err = float((vol[0].double() - ref).abs().max()) / float(ref.abs().max())
+    assert err <= 1e-5, err
