@@ -9,6 +9,7 @@ from .functional import (aggregate_views, aggregate_views_bilinear, backproject,
                          switch_pointcloud, ray_projection, rma_dense_weights, rma_points, scale_projections)
 from .module import RayMarchingAggregator, make_detector_class  # noqa: F401
 from .fusion import TSDFFusion  # noqa: F401
+from .tsdf_head import AtlasTSDFHead, tsdf_head_scale  # noqa: F401
 from . import distributed, synthetic  # noqa: F401
 
 __all__ = ["CnrmaError", "build", "load", "aggregate_views", "backproject", "dense_rma", "get_ray_parameter",

@@ -11,7 +11,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libcnrma_b200.so")
-SOURCES = ["cnrma_abi.cu", "cnrma_stage_a.cu", "cnrma_stage_a_list.cu", "cnrma_stage_a_bilinear.cu", "cnrma_stage_b.cu", "cnrma_backward.cu",
+SOURCES = ["cnrma_abi.cu", "cnrma_stage_a.cu", "cnrma_stage_a_list.cu", "cnrma_stage_a_bilinear.cu", "cnrma_tsdf_head.cu", "cnrma_stage_b.cu", "cnrma_backward.cu",
            "cnrma_handoff.cu", "cnrma_fusion.cu"]
 HEADERS = ["cnrma_common.cuh", "cnrma_internal.cuh", os.path.join("..", "..", "include", "cnrma_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false", "-std=c++17",
@@ -83,6 +83,12 @@ _SIGNATURES = {
                                         C.c_void_p]),
     "cnrma_aggregate_views_bilinear": (C.c_int, [C.POINTER(Grid), C.POINTER(Features), C.c_void_p, C.c_int64, C.c_float,
                                                  C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cnrma_tsdf_head_scale": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64,
+                                        C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cnrma_tsdf_head_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "cnrma_tsdf_head_scale_backward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "cnrma_selftest_count_division": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
     "cnrma_to_channels_last": (C.c_int, [C.POINTER(Features), C.c_void_p, C.c_void_p]),
     "cnrma_t_one": (C.c_float, [C.POINTER(Grid), C.c_double, C.c_int]),

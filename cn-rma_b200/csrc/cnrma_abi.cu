@@ -356,6 +356,43 @@ int cnrma_tsdf_integrate(const cnrma_grid *grid, const float *projections, int64
     return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
 }
 
+static bool head_dims_ok(int channels, int nx, int ny, int nz, int64_t stride_c, int64_t stride_v, const float *prev) {
+    if (channels <= 0 || channels > 1024 || nx <= 0 || ny <= 0 || nz <= 0 || stride_c <= 0 || stride_v <= 0) return false;
+    if ((int64_t)nx * ny * nz >= ((int64_t)1 << 31)) return false;
+    if (prev && ((nx | ny | nz) & 1)) return false;   // F.interpolate(scale_factor=2) doubles every extent (ah.py:45)
+    return true;
+}
+
+int cnrma_tsdf_head_scale(const void *x, int dtype, int channels, int nx, int ny, int nz, int64_t stride_c,
+                          int64_t stride_v, const float *weight, const float *prev, float label_smoothing,
+                          float sparse_threshold, float *tsdf, uint8_t *mask, void *stream) {
+    if (!x || !weight || !tsdf || (dtype != CNRMA_F32 && dtype != CNRMA_BF16)) return CNRMA_ERR_ARG;
+    if (!head_dims_ok(channels, nx, ny, nz, stride_c, stride_v, prev)) return CNRMA_ERR_ARG;
+    const int d = device_ok();
+    if (d != CNRMA_OK) return d;
+    const cudaError_t e = run_tsdf_head_scale(x, dtype, channels, nx, ny, nz, stride_c, stride_v, weight, prev,
+                                              label_smoothing, sparse_threshold, tsdf, mask,
+                                              static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
+}
+
+size_t cnrma_tsdf_head_workspace_bytes(int channels) { return channels > 0 ? tsdf_head_workspace_bytes(channels) : 0; }
+
+int cnrma_tsdf_head_scale_backward(const float *x, int channels, int nx, int ny, int nz, int64_t stride_c,
+                                   int64_t stride_v, const float *weight, const float *prev, const float *tsdf,
+                                   const float *grad_tsdf, float label_smoothing, float sparse_threshold, float *grad_x,
+                                   float *grad_weight, void *workspace, size_t workspace_bytes, void *stream) {
+    if (!x || !weight || !tsdf || !grad_tsdf || (!grad_x && !grad_weight)) return CNRMA_ERR_ARG;
+    if (!head_dims_ok(channels, nx, ny, nz, stride_c, stride_v, prev) || !(label_smoothing != 0.0f)) return CNRMA_ERR_ARG;
+    if (grad_weight && (!workspace || workspace_bytes < tsdf_head_workspace_bytes(channels))) return CNRMA_ERR_CAPACITY;
+    const int d = device_ok();
+    if (d != CNRMA_OK) return d;
+    const cudaError_t e = run_tsdf_head_backward(x, channels, nx, ny, nz, stride_c, stride_v, weight, prev, tsdf,
+                                                 grad_tsdf, label_smoothing, sparse_threshold, grad_x, grad_weight,
+                                                 workspace, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
+}
+
 int cnrma_rma_expand(int views, int height, int width, int grids, float threshold, const void *workspace,
                      float *weights, uint8_t *keep, void *stream) {
     if (!workspace || views <= 0 || height <= 0 || width <= 0 || grids <= 0) return CNRMA_ERR_ARG;

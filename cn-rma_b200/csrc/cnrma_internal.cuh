@@ -1,6 +1,8 @@
 // Internal launch interface between cnrma_abi.cu and the kernel translation units.
 #pragma once
 
+#include <algorithm>
+
 #include "cnrma_common.cuh"
 
 namespace cnrma {
@@ -56,6 +58,15 @@ size_t sample_workspace_bytes();
 cudaError_t run_sample_mask(int64_t n, int64_t k, unsigned long long seed, void *workspace, uint8_t *mask,
                             cudaStream_t stream);
 
+// cnrma_tsdf_head.cu
+cudaError_t run_tsdf_head_scale(const void *x, int dtype, int C, int nx, int ny, int nz, int64_t stride_c,
+                                int64_t stride_v, const float *weight, const float *prev, float ls, float thr,
+                                float *tsdf, uint8_t *mask, cudaStream_t stream);
+size_t tsdf_head_workspace_bytes(int C);
+cudaError_t run_tsdf_head_backward(const float *x, int C, int nx, int ny, int nz, int64_t stride_c, int64_t stride_v,
+                                   const float *weight, const float *prev, const float *tsdf, const float *grad_tsdf,
+                                   float ls, float thr, float *grad_x, float *grad_weight, void *workspace,
+                                   cudaStream_t stream);
 // cnrma_fusion.cu
 cudaError_t run_tsdf_integrate(const GridDev &g, const float *proj, int64_t proj_stride, int frames,
                                const float *const *depth_host, const float *const *color_host,

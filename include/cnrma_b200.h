@@ -260,6 +260,29 @@ int cnrma_tsdf_integrate(const cnrma_grid *grid, const float *projections, int64
                          const int64_t *const *label_ptrs_host, int height, int width, float trunc_margin, float *tsdf,
                          float *weight, float *color, int64_t *label, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * TSDF head hand-over: one scale of AtlasTSDFHead.forward, projects/mvsdetection/models/atlas_head.py:38-52 -- the
+ * producer of `scene_tsdf_004`, the volume cnrma_rma_march walks.
+ *   tsdf = tanh(sum_c weight[c] * x[c, v]) * label_smoothing; with prev (the coarser scale's output, extents
+ *   nx/2 x ny/2 x nz/2, nearest x2 upsampling): where !(|prev| < sparse_threshold): tsdf = sign(prev) * .999
+ *   x       f32 or bf16, element strides stride_c (channels) / stride_v (flat voxel index (x*ny+y)*nz+z):
+ *           NCDHW -> (nvox, 1); channels-last -> (1, C).  Voxels whose coarse parent is not surface are not read.
+ *   weight  f32 [C] device (the Conv3d(C,1,1,bias=False) kernel, ah.py:29);  prev NULL for the first scale
+ *   tsdf    f32 [nvox] out;  mask uint8 [nvox] out or NULL (= |prev| < thr, ah.py:47; all ones without prev)
+ * Floating-point row (the reference's cudnn reduction order is unspecified): parity 1e-5, mask exact outside a
+ * 1e-5 band around the threshold.
+ * cnrma_tsdf_head_scale_backward: autograd of the above for dL/dtsdf = grad_tsdf (f32 x only): grad_x (x's strides)
+ * and/or grad_weight [C] may be NULL; workspace (cnrma_tsdf_head_workspace_bytes) is needed for grad_weight.
+ * ------------------------------------------------------------------------------------------- */
+int cnrma_tsdf_head_scale(const void *x, int dtype, int channels, int nx, int ny, int nz, int64_t stride_c,
+                          int64_t stride_v, const float *weight, const float *prev, float label_smoothing,
+                          float sparse_threshold, float *tsdf, uint8_t *mask, void *stream);
+size_t cnrma_tsdf_head_workspace_bytes(int channels);
+int cnrma_tsdf_head_scale_backward(const float *x, int channels, int nx, int ny, int nz, int64_t stride_c,
+                                   int64_t stride_v, const float *weight, const float *prev, const float *tsdf,
+                                   const float *grad_tsdf, float label_smoothing, float sparse_threshold, float *grad_x,
+                                   float *grad_weight, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Dense per-sample view of the march records for parity tests: weights f32 [V*H*W*N] (0 where not kept,
  * i.e. rm.py:767 `weights * valid_final`) and keep uint8 [V*H*W*N].  NEUS mode only. */
 int cnrma_rma_expand(int views, int height, int width, int grids, float threshold, const void *workspace,

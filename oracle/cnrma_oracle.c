@@ -499,3 +499,33 @@ ORACLE_API void cnrma_oracle_tsdf_integrate(int nx, int ny, int nz, float voxel_
                 }
             }
 }
+
+/* ---- TSDF head, one scale ------------------------------------------------------
+ * models/atlas_head.py:38-52 for one decoder: tsdf = tanh(conv1x1x1(x)) * label_smoothing; with a previous scale,
+ * prev = nearest x2 upsample; where !(|prev| < sparse_threshold): tsdf = sign(prev) * .999.
+ * x planar [C, nvox] (NCDHW), weight [C], prev [nx/2, ny/2, nz/2] or NULL.  The channel dot product is accumulated
+ * in double: torch's conv kernel sums in an unspecified order, so parity on this row is a tolerance (see the test),
+ * with the mask compared outside a band around the threshold.  mask (optional) = |prev| < thr as 0/1. */
+ORACLE_API void cnrma_oracle_tsdf_head_scale(int C, int nx, int ny, int nz, const float *x, const float *weight,
+                                             const float *prev, float label_smoothing, float sparse_threshold,
+                                             float *tsdf, uint8_t *mask) {
+    size_t nvox = (size_t)nx * ny * nz;
+    int py = ny / 2, pz = nz / 2;
+#pragma omp parallel for schedule(static)
+    for (int ix = 0; ix < nx; ++ix)
+        for (int iy = 0; iy < ny; ++iy)
+            for (int iz = 0; iz < nz; ++iz) {
+                size_t i = ((size_t)ix * ny + iy) * nz + iz;
+                double acc = 0.0;
+                for (int c = 0; c < C; ++c) acc += (double)weight[c] * (double)x[(size_t)c * nvox + i];
+                float t = (float)tanh((double)(float)acc) * label_smoothing;
+                uint8_t m = 1;
+                if (prev) {
+                    float p = prev[((size_t)(ix / 2) * py + (iy / 2)) * pz + (iz / 2)];
+                    m = fabsf(p) < sparse_threshold;
+                    if (!m) t = (float)((p > 0.0f) - (p < 0.0f)) * 0.999f;
+                }
+                tsdf[i] = t;
+                if (mask) mask[i] = m;
+            }
+}

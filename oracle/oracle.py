@@ -241,3 +241,32 @@ def tsdf_integrate(voxel_dim, voxel_size, origin, projection, depth, trunc_margi
                                       None if keep[4] is None else _p(keep[4]), C.c_float(trunc_margin),
                                       _p(tsdf), _p(weight), None if color is None else _p(color),
                                       None if label is None else _p(label))
+
+
+def tsdf_head_scale(x, weight, prev, label_smoothing, sparse_threshold):
+    """One decoder of AtlasTSDFHead.forward (models/atlas_head.py:38-52): x [C,nx,ny,nz] f32, weight [C],
+    prev [nx/2,ny/2,nz/2] or None -> (tsdf [nx,ny,nz] f32, mask [nx,ny,nz] bool)."""
+    x = _f(x)
+    c, nx, ny, nz = x.shape
+    w = _f(weight).reshape(c)
+    p = None if prev is None else _f(prev)
+    if p is not None:
+        assert p.shape == (nx // 2, ny // 2, nz // 2) and nx % 2 == 0 and ny % 2 == 0 and nz % 2 == 0
+    tsdf = np.empty((nx, ny, nz), np.float32)
+    mask = np.empty((nx, ny, nz), np.uint8)
+    lib().cnrma_oracle_tsdf_head_scale(C.c_int(c), C.c_int(nx), C.c_int(ny), C.c_int(nz), _p(x), _p(w),
+                                       None if p is None else _p(p), C.c_float(label_smoothing),
+                                       C.c_float(0.0 if sparse_threshold is None else sparse_threshold), _p(tsdf), _p(mask))
+    return tsdf, mask.astype(bool)
+
+
+def tsdf_head(xs, weights, label_smoothing, sparse_threshold):
+    """All scales, coarse to fine (atlas_head.py:38-52): returns ([tsdf_i], [mask_i for i>0])."""
+    out, masks, prev = [], [], None
+    for i, (x, w) in enumerate(zip(xs, weights)):
+        t, m = tsdf_head_scale(x, w, prev, label_smoothing, sparse_threshold[i - 1] if i > 0 else None)
+        out.append(t)
+        if i > 0:
+            masks.append(m)
+        prev = t
+    return out, masks
