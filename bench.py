@@ -383,6 +383,11 @@ def main():
         torch.cuda.synchronize()
         handoff = {"ms_per_scene": h0.elapsed_time(h1) / 10, "rows_kept": int(sel[0][0].shape[0]), "rows_total": m_rows,
                    "what": "sample mask (device) + march + fill of the kept rows only, offset added; excludes Stage A"}
+        if not args.no_e2e:
+            del sel
+            handoff["e2e"] = run_e2e(args, cn, sc, feats, proj, tsdf, dev, world, m_rows, handoff_rows=500000)
+            handoff["e2e"]["what"] = ("the e2e leg with the lift fused with the hand-off: host features in, Stage A volume "
+                                      "+ the 500000 kept point rows out (the un-sampled cloud is never materialised)")
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
@@ -452,12 +457,13 @@ def run_view_sharded(args, cn, dev, rank, world):
         dist.destroy_process_group()
 
 
-def run_e2e(args, cn, sc, feats, proj, tsdf, dev, world, m_rows):
+def run_e2e(args, cn, sc, feats, proj, tsdf, dev, world, m_rows, handoff_rows=None):
     """Same step through the public host API with HOST buffers: every step copies its inputs from pinned host
     memory to the device and its results (volume, count, points) back to pinned host memory.  Three streams
     (copy-in, compute, copy-out) with double-buffered device inputs, so the next scene's upload and the previous
     scene's download overlap with the kernels; timed with CUDA events from the first upload to the last download,
-    max over ranks."""
+    max over ranks.  With `handoff_rows` the lift is fused with the detector's point-cloud hand-off (rm.py:339-407):
+    only the kept rows are produced and downloaded."""
     import torch
     import torch.distributed as dist
     V, C, H, W = sc.views, sc.channels, sc.height, sc.width
@@ -468,7 +474,7 @@ def run_e2e(args, cn, sc, feats, proj, tsdf, dev, world, m_rows):
     nx, ny, nz = sc.voxel_dim
     h_vol = torch.empty((1, nx, ny, nz, C), dtype=torch.float32).pin_memory()
     h_cnt = torch.empty((1, 1, nx, ny, nz), dtype=torch.int32).pin_memory()
-    h_pts = torch.empty((int(m_rows * 1.05) + 1024, 3 + C), dtype=torch.float32).pin_memory()
+    h_pts = torch.empty((handoff_rows or int(m_rows * 1.05) + 1024, 3 + C), dtype=torch.float32).pin_memory()
     ag = cn.RayMarchingAggregator(sc.voxel_size, sc.voxel_dim, origin=sc.origin.tolist(), backbone2d_stride=sc.stride,
                                   neus_threshold=args.threshold)
     s_in, s_cmp, s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
@@ -494,9 +500,17 @@ def run_e2e(args, cn, sc, feats, proj, tsdf, dev, world, m_rows):
             for v in range(V):
                 ag.aggregate_2d_features(sl["proj"][v], d_feats[v])
             ag.clear_3d_features()
-            ag.aggregate_2d_features_ray_marching(h_proj, d_feats, sl["tsdf"])   # cameras also known on the host
+            if handoff_rows is None:
+                ag.aggregate_2d_features_ray_marching(h_proj, d_feats, sl["tsdf"])   # cameras also known on the host
+                pts = ag.points_detection[0]
+            else:
+                draw = lambda n: cn.sample_points_device(n, handoff_rows, 1234 + k, dev)
+                co, fe = cn.rma_points_selected(h_proj, d_feats, sl["tsdf"], sc.voxel_dim, sc.voxel_size, sc.origin,
+                                                sc.stride, offsets=[[0.0, 0.0, 0.0]], masks=[draw], grids=sc.grids,
+                                                threshold=args.threshold)
+                pts = co[0]._base if co[0]._base is not None else torch.cat((co[0], fe[0]), 1)
             sl["used"].record(s_cmp)
-            pts, vol, cnt = ag.points_detection[0], ag.volume, ag._sum[1]
+            vol, cnt = ag.volume, ag._sum[1]
         with torch.cuda.stream(s_out):
             s_out.wait_stream(s_cmp)
             h_vol.copy_(vol.permute(0, 2, 3, 4, 1), non_blocking=True)
@@ -534,8 +548,9 @@ def run_e2e(args, cn, sc, feats, proj, tsdf, dev, world, m_rows):
     return {"value": world * sc.voxel_views / (ms * 1e-3), "unit": "voxel*views/s", "ms_per_step": ms,
             "scenes_per_s": world / (ms * 1e-3), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
             "pcie_gbs": (h2d + d2h) / ms / 1e6,
-            "api": "RayMarchingAggregator (host mirror of the reference detector's aggregation methods); "
-                   "copy-in / compute / copy-out on three streams"}
+            "api": "RayMarchingAggregator (host mirror of the reference detector's aggregation methods)"
+                   + ("" if handoff_rows is None else " + rma_points_selected (lift fused with switch_pointcloud)")
+                   + "; copy-in / compute / copy-out on three streams"}
 
 
 def run_cpu_baseline(args, sc):

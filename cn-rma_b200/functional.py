@@ -737,7 +737,8 @@ def switch_pointcloud(points, offsets, max_points=None, masks=None, rng=None):
 def rma_points_selected(projections, features, tsdf, voxel_dim, voxel_size, origin, stride, offsets, max_points=None,
                         masks=None, rng=None, grids=300, mode="neus", threshold=None, depth_points=None):
     """aggregate_2d_features_ray_marching (rm.py:260-307) fused with switch_pointcloud (rm.py:339-407): the march
-    runs as usual, M is read back, the keep mask is drawn (or taken from `masks`), and the fill kernel produces ONLY
+    runs as usual, M is read back, the keep mask is drawn (or taken from `masks`: per batch element a mask or a
+    callable `n -> mask`), and the fill kernel produces ONLY
     the kept rows, offset already added -- the un-sampled point cloud (M x (3+C) floats) is never written.
 
     Returns (coords list of [Nsel,3], features list of [Nsel,C]) like switch_pointcloud."""
@@ -759,6 +760,8 @@ def rma_points_selected(projections, features, tsdf, voxel_dim, voxel_size, orig
             n = int(_read_result(m).rows)
             mask = masks[b] if masks is not None else (sample_points(n, max_points, rng) if max_points is not None
                                                        else None)
+            if callable(mask):                      # drawn once M is known, e.g. lambda n: sample_points_device(n, ...)
+                mask = mask(n)
             if mask is None:
                 mask_dev, n_sel = torch.ones(n, dtype=torch.bool, device=device), n
             else:
