@@ -100,8 +100,22 @@ int cnrma_aggregate_views(const cnrma_grid *grid, const cnrma_features *features
     int max_chunk_vecs = 0;
     if (const char *env = std::getenv("CNRMA_AGG_CHUNK_BYTES")) max_chunk_vecs = std::atoi(env);
     const GridDev g = to_dev(*grid);
-    for (int v0 = 0; v0 < features->views || v0 == 0; v0 += kMaxViewsPerLaunch) {
-        const int nv = (features->views - v0 < kMaxViewsPerLaunch) ? (features->views - v0) : kMaxViewsPerLaunch;
+    // Views go out in batches that accumulate into the volume in view order (the fp32 chain of the reference's
+    // `self.volume + volume` loop is unchanged).  Short rows with many views are split into batches the list kernel
+    // can serve (DESIGN.md "K_A'"): the extra read-modify-write of the volume costs far less than the per-row
+    // overhead of the TMA kernel on rows below 512 bytes.
+    int batch = kMaxViewsPerLaunch;
+    const int row_bytes = features->channels * (features->dtype == CNRMA_BF16 ? 2 : 4);
+    if (row_bytes < 512 && features->views > kListViewsMax) {
+        int per = kListViewsBatch;
+        if (const char *env = std::getenv("CNRMA_AGG_LIST_VIEWS")) per = std::atoi(env);   // tuning aid
+        if (per >= 1 && per <= kListViewsMax) {
+            const int nbatch = (features->views + per - 1) / per;
+            batch = (features->views + nbatch - 1) / nbatch;
+        }
+    }
+    for (int v0 = 0; v0 < features->views || v0 == 0; v0 += batch) {
+        const int nv = (features->views - v0 < batch) ? (features->views - v0) : batch;
         uint32_t fl = flags & (CNRMA_AGG_ACCUMULATE | CNRMA_AGG_COUNT_F32);
         if (v0 > 0) fl |= CNRMA_AGG_ACCUMULATE;
         if ((flags & CNRMA_AGG_MEAN) && v0 + nv == features->views) fl |= CNRMA_AGG_MEAN;

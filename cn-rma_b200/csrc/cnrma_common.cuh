@@ -122,6 +122,13 @@ struct Vec16<float> {
         r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
         return r;
     }
+    // the 16 bytes as loaded; widened later, so that several loads can be in flight before the first conversion
+    __device__ __forceinline__ static uint4 load_raw(const float *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+    __device__ __forceinline__ static Vec16 widen(const uint4 t) {
+        Vec16 r;
+        r.v[0] = __uint_as_float(t.x); r.v[1] = __uint_as_float(t.y); r.v[2] = __uint_as_float(t.z); r.v[3] = __uint_as_float(t.w);
+        return r;
+    }
 };
 
 template <>
@@ -132,6 +139,7 @@ struct Vec16<__nv_bfloat16> {
         return widen(__ldg(reinterpret_cast<const uint4 *>(p)));
     }
     __device__ __forceinline__ static Vec16 load_shared(const void *p) { return widen(*reinterpret_cast<const uint4 *>(p)); }
+    __device__ __forceinline__ static uint4 load_raw(const __nv_bfloat16 *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
     __device__ __forceinline__ static Vec16 widen(const uint4 t) {
         Vec16 r;
         const uint32_t w[4] = {t.x, t.y, t.z, t.w};

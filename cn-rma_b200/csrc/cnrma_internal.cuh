@@ -58,6 +58,9 @@ size_t sample_workspace_bytes();
 cudaError_t run_sample_mask(int64_t n, int64_t k, unsigned long long seed, void *workspace, uint8_t *mask,
                             cudaStream_t stream);
 
+constexpr int kListViewsMax = 96;     // the list kernel's per-voxel lists stop paying beyond this many views per launch
+constexpr int kListViewsBatch = 63;   // batch size used to split longer view lists (32 voxels x 63 entries fit a warp's 8 KB)
+
 // cnrma_tsdf_head.cu
 cudaError_t run_tsdf_head_scale(const void *x, int dtype, int C, int nx, int ny, int nz, int64_t stride_c,
                                 int64_t stride_v, const float *weight, const float *prev, float ls, float thr,

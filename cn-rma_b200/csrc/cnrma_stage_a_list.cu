@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kListThreads) aggregate_views_list_kernel(cons
 #pragma unroll
             for (int o = 16; o >= G; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
             for (int k = 0; k < nmax; k += kListUnroll) {
-                V16 val[kListUnroll][VPL];
+                uint4 raw[kListUnroll][VPL];
 #pragma unroll
                 for (int uu = 0; uu < kListUnroll; ++uu) {
                     if (k + uu < n) {
@@ -150,16 +150,18 @@ __global__ void __launch_bounds__(kListThreads) aggregate_views_list_kernel(cons
                                     : (sView[e >> 20] + (int64_t)((e >> 10) & 1023u) * p.stride_y_bytes +
                                        (int64_t)(e & 1023u) * p.stride_x_bytes + lig * 16);
 #pragma unroll
-                        for (int q = 0; q < VPL; ++q) val[uu][q] = V16::load(reinterpret_cast<const T *>(src + q * G * 16));
+                        for (int q = 0; q < VPL; ++q) raw[uu][q] = V16::load_raw(reinterpret_cast<const T *>(src + q * G * 16));
                     }
                 }
 #pragma unroll
                 for (int uu = 0; uu < kListUnroll; ++uu) {
                     if (k + uu < n) {
 #pragma unroll
-                        for (int q = 0; q < VPL; ++q)
+                        for (int q = 0; q < VPL; ++q) {
+                            const V16 val = V16::widen(raw[uu][q]);
 #pragma unroll
-                            for (int e = 0; e < E; ++e) acc[q][e] = __fadd_rn(acc[q][e], val[uu][q].v[e]);
+                            for (int e = 0; e < E; ++e) acc[q][e] = __fadd_rn(acc[q][e], val.v[e]);
+                        }
                     }
                 }
             }
