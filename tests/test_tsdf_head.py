@@ -78,7 +78,7 @@ def test_mirror_parameters_and_losses_match_reference(head):
     masks = [torch.from_numpy(np.abs(_upsampled(g[f"tsdf{i - 1}"])) < np.float32(g["thr"][i - 1])) for i in (1, 2)]
     losses = m.losses(output, masks, targets)
     for i, k in enumerate(g["keys"]):
-        assert abs(float(losses["tsdf_loss_" + k]) - float(g[f"loss{i}"])) <= 1e-6
+        assert abs(losses["tsdf_loss_" + k].item() - float(g[f"loss{i}"])) <= 1e-6
 
 
 def test_head_needs_cuda():
@@ -147,7 +147,7 @@ def test_gpu_head_forward_losses_and_gradients_vs_reference(cn, head):
         for i, k in enumerate(g["keys"]):
             ok = np.ones(g[f"tsdf{i}"].shape, bool) if i == 0 else _outside_band(g[f"tsdf{i - 1}"], g["thr"][i - 1])
             assert np.max(np.abs(out["scene_tsdf_" + k].detach().cpu().numpy() - g[f"tsdf{i}"])[ok]) <= TOL
-            assert abs(float(losses["tsdf_loss_" + k]) - float(g[f"loss{i}"])) <= 1e-5
+            assert abs(losses["tsdf_loss_" + k].item() - float(g[f"loss{i}"])) <= 1e-5
             gx, gw = xs[i].grad.cpu().numpy(), m.decoders[i].weight.grad.cpu().numpy().reshape(-1)
             assert np.max(np.abs(gx - g[f"grad_x{i}"])) <= TOL * max(1e-30, np.max(np.abs(g[f"grad_x{i}"]))), (layout, i)
             assert np.max(np.abs(gw - g[f"grad_w{i}"])) <= TOL * max(1e-30, np.max(np.abs(g[f"grad_w{i}"]))), (layout, i)
