@@ -133,7 +133,9 @@ def make_detector_class(ray_marching_cls):
     """mmdet adapter: `RayMarchingB200 = make_detector_class(RayMarching)` gives a detector whose five
     aggregation methods and three state attributes come from RayMarchingAggregator while everything else
     (networks, losses, data conversion) stays the reference's.  Register it under its own type name; see
-    INTEGRATION.md.  Not executable in this repository's test environment (mmdet / MinkowskiEngine absent)."""
+    INTEGRATION.md.  tests/test_adapter_reference_flow.py runs the reference's unmodified forward_train / forward_test on
+    such a class (stub networks; CPU stand-ins for the kernels, since the reference tree and a GPU are never on one box)
+    and compares with the reference class itself."""
 
     class RayMarchingB200(ray_marching_cls):
         initialize_volume = RayMarchingAggregator.initialize_volume
