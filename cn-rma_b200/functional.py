@@ -14,6 +14,7 @@ PyTorch is used for device memory, streams and the 4x4 LAPACK inverse the refere
 live on a CUDA device and the library must be built.
 """
 import ctypes as C
+import types
 
 import torch
 
@@ -581,11 +582,8 @@ def rma_dense_weights(projections, height, width, tsdf, voxel_dim, voxel_size, o
     """Parity surface for rm.py:765-767: (weights * valid_final, valid_final), each [V,H,W,N], batch 1."""
     lib = _lib.load()
     device = torch.device(device) if device is not None else tsdf.device
-
-    class _Shape:
-        pass
-    fs = _Shape()
-    fs.device, fs.V, fs.H, fs.W = device, projections.shape[0], int(height), int(width)
+    # _march only reads the geometry of the feature stack (no feature data is touched by the march)
+    fs = types.SimpleNamespace(device=device, V=projections.shape[0], H=int(height), W=int(width))
     P_scaled = scale_projections(projections, stride)
     grid = _lib.make_grid(voxel_dim, voxel_size, _origin3(origin))
     with torch.cuda.device(device):
