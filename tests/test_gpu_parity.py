@@ -467,3 +467,30 @@ def _check_bilinear(cn, sc, dtype):
     ref = (acc / cnt.view(1, -1).clamp_min(1).double()).view(sc.channels, nx, ny, nz)
     err = float((vol[0].double() - ref).abs().max()) / float(ref.abs().max())
     assert err <= 1e-5, err
+
+
+@pytest.mark.parametrize("views,channels,dtype", [(130, 8, None), (200, 16, torch.bfloat16), (97, 64, None)])
+def test_many_views_short_rows_batches(cn, views, channels, dtype):
+    """More than 96 views of rows below 512 bytes: the view list goes out as list-kernel batches that accumulate
+    into the volume in view order (cnrma_abi.cu) -- still the reference's fp32 chain bit for bit.  Also the
+    kernels forced one way or the other must agree."""
+    import os
+    sc = cn.synthetic.make_scene(dict(views=views, channels=channels, height=18, width=24, voxel_dim=(14, 12, 6),
+                                   voxel_size=0.35, tsdf="room", grids=40, dtype="f32"), seed=3)
+    p, f, _ = _scene_tensors(sc, dtype=dtype)
+    feats = f.float().cpu().numpy()[:, 0]
+    ovol, ocnt = oracle.aggregate_views(sc.projections, feats, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride, mean=True)
+    results = []
+    for kernel in (None, "list", "tma"):
+        if kernel is None:
+            os.environ.pop("CNRMA_AGG_KERNEL", None)
+        else:
+            os.environ["CNRMA_AGG_KERNEL"] = kernel
+        try:
+            vol, cnt, _ = cn.aggregate_views(p, f, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride, mean=True)
+        finally:
+            os.environ.pop("CNRMA_AGG_KERNEL", None)
+        assert np.array_equal(cnt[0, 0].cpu().numpy(), ocnt), kernel
+        assert np.array_equal(vol[0].cpu().numpy().view(np.uint32), ovol.view(np.uint32)), kernel
+        results.append(vol)
+    assert int(ocnt.max()) > 8
