@@ -406,8 +406,8 @@ def main():
         "stage_ms": {"stage_a": ms_a, "march": ms_march, "fill": ms_fill},
         "kernels": kernels, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
         "handoff": handoff,
-        # aggregate_views | tsdf_sigmoid, dist_boundary, 3 x dist_pass, march_neus, scan_blocks | fill_rows_tma
-        "gpu_launches": (9 if args.stage == "both" else (1 if args.stage == "a" else 8)) * args.steps,
+        # aggregate_views | tsdf_prepare_slab, dist_pass (x), march_neus, scan_blocks | fill_rows_tma
+        "gpu_launches": (6 if args.stage == "both" else (1 if args.stage == "a" else 5)) * args.steps,
     }
     print(json.dumps(line))
     if world > 1:

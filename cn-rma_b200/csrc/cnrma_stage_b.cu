@@ -10,6 +10,8 @@
 //   fill   one CTA per 256 rays: per-ray offsets by warp scan, then each warp streams its rays' rows --
 //          the pixel's feature vector is read once into registers and written once per kept sample,
 //          scaled by w/mean, as coalesced row segments.
+#include <cstdlib>
+
 #include "cnrma_internal.cuh"
 
 namespace cnrma {
@@ -178,6 +180,67 @@ __global__ void __launch_bounds__(256) dist_pass_kernel(GridDev g, int axis, con
         if (pos + d < n) best = min(best, max(d, (int)in[v + d * stride]));
     }
     out[v] = (uint8_t)best;
+}
+
+// Fused pre-pass for grids whose (y, z) plane fits shared memory: one CTA per x index tabulates s for its plane,
+// runs the boundary test (on the raw TSDF bits: equal bits give equal s; unequal bits with equal s only make the
+// field more conservative) and the z and y passes of the distance transform in shared memory.  With the x pass that
+// follows, the pre-pass is two launches instead of five (the march of cfg 2 is ~280 us; every launch costs 5-7 us).
+constexpr int kSlabThreads = 1024;
+__global__ void __launch_bounds__(kSlabThreads) tsdf_prepare_slab_kernel(GridDev g, const float *__restrict__ tsdf,
+                                                                         float *__restrict__ sig, uint8_t *__restrict__ out,
+                                                                         cnrma_rma_result *result) {
+    extern __shared__ uint8_t slab[];
+    const int plane = g.ny * g.nz;
+    uint8_t *A = slab, *B = slab + plane;
+    const int x = blockIdx.x;
+    if (x == 0 && threadIdx.x == 0) {   // the march that follows adds to `overflow`; the scan kernel writes the rest
+        result->rows = 0;
+        result->weight_sum = 0.0;
+        result->mean = 0.0f;
+        result->overflow = 0;
+    }
+    const float *base = tsdf + (int64_t)x * plane;
+    for (int i = threadIdx.x; i < plane; i += kSlabThreads) {
+        const int y = i / g.nz, z = i - y * g.nz;
+        const float tv = __ldg(base + i);
+        sig[(int64_t)x * plane + i] = sigmoid_neg(tv);
+        if (out != nullptr) {
+            bool boundary = (x == 0 || y == 0 || z == 0 || x == g.nx - 1 || y == g.ny - 1 || z == g.nz - 1);
+            if (!boundary) {
+                const uint32_t ref = __float_as_uint(tv);
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx)
+#pragma unroll
+                    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                        for (int dz = -1; dz <= 1; ++dz)
+                            boundary = boundary || (__float_as_uint(__ldg(base + dx * plane + (y + dy) * g.nz + (z + dz))) != ref);
+            }
+            A[i] = boundary ? 0 : kDistCap;
+        }
+    }
+    if (out == nullptr) return;
+    __syncthreads();
+    for (int i = threadIdx.x; i < plane; i += kSlabThreads) {   // along z
+        const int y = i / g.nz, z = i - y * g.nz;
+        int best = A[i];
+        for (int d = 1; d < best; ++d) {
+            if (z - d >= 0) best = min(best, max(d, (int)A[i - d]));
+            if (z + d < g.nz) best = min(best, max(d, (int)A[i + d]));
+        }
+        B[i] = (uint8_t)best;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < plane; i += kSlabThreads) {   // along y
+        const int y = i / g.nz;
+        int best = B[i];
+        for (int d = 1; d < best; ++d) {
+            if (y - d >= 0) best = min(best, max(d, (int)B[i - d * g.nz]));
+            if (y + d < g.ny) best = min(best, max(d, (int)B[i + d * g.nz]));
+        }
+        out[(int64_t)x * plane + i] = (uint8_t)best;
+    }
 }
 
 __device__ __forceinline__ VoxelMap make_voxel_map(const GridDev &g) {
@@ -736,22 +799,43 @@ cudaError_t run_march(const GridDev &g, const float *pinv, int V, int H, int W, 
     p.result = result;
     p.dist = nullptr;
     p.sig = nullptr;
-    cudaError_t err = cudaMemsetAsync(result, 0, sizeof(cnrma_rma_result), stream);
-    if (err != cudaSuccess) return err;
+    cudaError_t err = cudaSuccess;
+    const int nvox = g.nx * g.ny * g.nz;
+    const size_t slab_bytes = 2 * (size_t)g.ny * g.nz;
+    const bool slab = mode == CNRMA_MARCH_NEUS && slab_bytes <= 96 * 1024 && std::getenv("CNRMA_MARCH_UNFUSED_PREPASS") == nullptr;
+    if (!slab) {
+        err = cudaMemsetAsync(result, 0, sizeof(cnrma_rma_result), stream);
+        if (err != cudaSuccess) return err;
+    }
     if (mode == CNRMA_MARCH_NEUS) {
-        const int nvox = g.nx * g.ny * g.nz;
         const unsigned vb = (unsigned)((nvox + 255) / 256);
         float *sig = reinterpret_cast<float *>(base + ws.off_sigmoid);
-        tsdf_sigmoid_kernel<<<vb, 256, 0, stream>>>(tsdf, nvox, sig);
+        uint8_t *d0 = reinterpret_cast<uint8_t *>(base + ws.off_dist);
+        uint8_t *d1 = d0 + nvox;
         p.sig = sig;
-        if (thr > 0.0f) {
-            uint8_t *d0 = reinterpret_cast<uint8_t *>(base + ws.off_dist);
-            uint8_t *d1 = d0 + nvox;
-            dist_boundary_kernel<<<vb, 256, 0, stream>>>(g, sig, d0);
-            dist_pass_kernel<<<vb, 256, 0, stream>>>(g, 2, d0, d1);
-            dist_pass_kernel<<<vb, 256, 0, stream>>>(g, 1, d1, d0);
-            dist_pass_kernel<<<vb, 256, 0, stream>>>(g, 0, d0, d1);
-            p.dist = d1;
+        if (slab) {
+            static thread_local int attr_dev = -1;
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (attr_dev != dev) {
+                err = cudaFuncSetAttribute(tsdf_prepare_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+                if (err != cudaSuccess) return err;
+                attr_dev = dev;
+            }
+            tsdf_prepare_slab_kernel<<<(unsigned)g.nx, kSlabThreads, slab_bytes, stream>>>(g, tsdf, sig, thr > 0.0f ? d0 : nullptr, result);
+            if (thr > 0.0f) {
+                dist_pass_kernel<<<vb, 256, 0, stream>>>(g, 0, d0, d1);
+                p.dist = d1;
+            }
+        } else {
+            tsdf_sigmoid_kernel<<<vb, 256, 0, stream>>>(tsdf, nvox, sig);
+            if (thr > 0.0f) {
+                dist_boundary_kernel<<<vb, 256, 0, stream>>>(g, sig, d0);
+                dist_pass_kernel<<<vb, 256, 0, stream>>>(g, 2, d0, d1);
+                dist_pass_kernel<<<vb, 256, 0, stream>>>(g, 1, d1, d0);
+                dist_pass_kernel<<<vb, 256, 0, stream>>>(g, 0, d0, d1);
+                p.dist = d1;
+            }
         }
         err = cudaGetLastError();
         if (err != cudaSuccess) return err;
