@@ -482,6 +482,7 @@ struct FillParams {
     float *wsum, *wtot;   // scatter variant
     const void *views[kMaxViewsPerLaunch];
     int view_base;        // first view of this launch
+    int stage_half;       // packed kernel: bytes per staging half (two per warp)
 };
 
 __device__ __forceinline__ void record_position(const FillParams &p, const float o[3], const float d[3], float fi,
@@ -852,6 +853,153 @@ cudaError_t run_march(const GridDev &g, const float *pinv, int V, int H, int W, 
     return cudaGetLastError();
 }
 
+// ---- fill, short rows ------------------------------------------------------------------------------------
+// The reference's own maps have 32 channels: a row is 140 bytes and a ray keeps ~6 of them, so in the kernel above the
+// per-ray work (the ray of the pixel -- computed by all 32 lanes for the same ray --, one small bulk store and its
+// head / tail fix-ups per ray) outweighs the rows themselves (ref test grid: 21 % of the HBM peak).  Here the per-ray
+// quantities are computed lane <-> ray once per warp and shuffled, and the rows of consecutive rays -- contiguous in
+// the output -- share staging buffers: two 4 KB halves per warp, filled across rays and pushed with one bulk store
+// when full, so the store of one half overlaps the assembly of the other.  Same arithmetic, same bits.
+constexpr int kHalfStageBytes = kStageBytes / 2;
+constexpr int kPackedRowBytesMax = 600;   // rows up to this size take the packed kernel (measured: see DESIGN.md K_B3)
+
+template <typename T, int NJ>
+__global__ void __launch_bounds__(kRayThreads) fill_rows_packed_kernel(const __grid_constant__ FillParams p) {
+    extern __shared__ __align__(128) unsigned char stage_raw[];
+    __shared__ int s_warp_rows[kRayThreads / kWarp];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half_bytes = p.stage_half;   // two halves per warp
+    unsigned char *stage_base = stage_raw + (size_t)warp * 2 * half_bytes;
+    const int hw = p.H * p.W;
+    const int64_t ray0 = (int64_t)p.view_base * hw + (int64_t)blockIdx.x * kRayThreads;
+    const int64_t my_ray = ray0 + threadIdx.x;
+    const int64_t ray_end = (int64_t)(p.view_base + p.V) * hw;
+    const int my_cnt = (my_ray < ray_end && my_ray < p.rays) ? p.counts[my_ray] : 0;
+    int incl = my_cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) s_warp_rows[warp] = incl;
+    __syncthreads();
+    int64_t base = p.blk_off[ray0 / kRayThreads];
+    for (int i = 0; i < warp; ++i) base += s_warp_rows[i];
+    const int64_t my_off = base + (incl - my_cnt);
+    // rows beyond the output capacity are dropped (speculative launches): clamp every ray's count once
+    const int my_keep = (int)min((int64_t)my_cnt, max((int64_t)0, p.capacity - my_off));
+    const int64_t warp_off = __shfl_sync(0xffffffffu, my_off, 0);       // the warp's rows are contiguous from here
+    unsigned char *const warp_gbase = reinterpret_cast<unsigned char *>(p.rows) + warp_off * (int64_t)((p.C + (p.normalize ? 3 : 4)) * 4);
+    int rows_done = 0;                                                  // rows of this warp already staged
+    const float mean = p.normalize ? __ldg(p.mean) : 1.0f;
+    const int col0 = p.normalize ? 3 : 4;
+    const int cols = p.C + col0;
+    const int row_bytes = cols * 4;
+    const int rows_per_stage = (half_bytes - 16) / row_bytes;
+
+    // lane <-> ray: the ray of my pixel and the address of its feature vector
+    float mo[3] = {0.0f, 0.0f, 0.0f}, md[3] = {0.0f, 0.0f, 0.0f};
+    const T *my_feat = nullptr;
+    if (my_keep > 0) {
+        const int view = (int)(my_ray / hw);
+        const int pix = (int)(my_ray % hw);
+        const int u = pix % p.W, v = pix / p.W;
+        ray_of_pixel(p.pinv + 16 * view, u, v, mo, md);
+        my_feat = static_cast<const T *>(p.views[view - p.view_base]) + (int64_t)v * p.stride_y + (int64_t)u * p.stride_x;
+    }
+
+    int sbuf = 0, srows = 0, h = 0;        // warp-uniform staging state: half in use, rows in it, byte offset mod 16
+    unsigned char *gbase = nullptr;        // global address of the first row in the stage
+    auto flush = [&]() {
+        float *stage = reinterpret_cast<float *>(stage_base + sbuf * half_bytes);
+        const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(stage);
+        const int hw4 = h >> 2;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        const int total = srows * row_bytes;
+        const int a0 = (h + 15) & ~15;
+        const int a1 = (h + total) & ~15;
+        if (lane == 0) {
+            if (a1 > a0)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gbase - h + a0),
+                             "r"(stage_addr + (uint32_t)a0), "r"((uint32_t)(a1 - a0))
+                             : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");      // one group per flush, possibly empty
+        }
+        const int head = (min(a0, h + total) - h) >> 2;
+        const int tail_lo = max(a1, a0);
+        const int tail = (h + total > tail_lo) ? ((h + total - tail_lo) >> 2) : 0;
+        if (lane < head) reinterpret_cast<float *>(gbase)[lane] = stage[hw4 + lane];
+        if (lane < tail) reinterpret_cast<float *>(gbase - h + tail_lo)[lane] = stage[(tail_lo >> 2) + lane];
+        sbuf ^= 1;
+        srows = 0;
+        // the other half was pushed one flush ago: its bulk store must have finished reading before it is refilled
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+    };
+
+    for (int r = 0; r < 32; ++r) {
+        const int cnt = __shfl_sync(0xffffffffu, my_keep, r);
+        if (cnt == 0) continue;
+        const int64_t ray = ray0 + warp * 32 + r;
+        float o[3], d[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            o[a] = __shfl_sync(0xffffffffu, mo[a], r);
+            d[a] = __shfl_sync(0xffffffffu, md[a], r);
+        }
+        const T *feat = reinterpret_cast<const T *>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(my_feat), r));
+        float f[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int c = j * 32 + lane;
+            f[j] = (c < p.C) ? load_feat<T>(feat + c) : 0.0f;
+        }
+        for (int k0 = 0; k0 < cnt; k0 += 32) {
+            const int nk = min(32, cnt - k0);
+            float wk = 0.0f, wraw = 0.0f, pos[3] = {0.0f, 0.0f, 0.0f};
+            if (lane < nk) {
+                wraw = __ldg(p.rec_w + (int64_t)(k0 + lane) * p.rays + ray);
+                const float fi = __ldg(p.rec_i + (int64_t)(k0 + lane) * p.rays + ray);
+                record_position(p, o, d, fi, pos);
+                wk = p.normalize ? __fdiv_rn(wraw, mean) : 1.0f;   // weights / mean(weights), rm.py:303
+            }
+            int k = 0;
+            while (k < nk) {
+                if (srows == 0) {   // rays of a warp own consecutive output rows, so a stage simply continues where the last ended
+                    gbase = warp_gbase + (int64_t)rows_done * row_bytes;
+                    h = (int)(reinterpret_cast<uintptr_t>(gbase) & 15);
+                }
+                float *stage = reinterpret_cast<float *>(stage_base + sbuf * half_bytes);
+                const int hw4 = h >> 2;
+                const int nb = min(rows_per_stage - srows, nk - k);
+                for (int kk = 0; kk < nb; ++kk) {
+                    const float wn = __shfl_sync(0xffffffffu, wk, k + kk);
+                    float *row = stage + hw4 + (srows + kk) * cols + col0;
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        const int c = j * 32 + lane;
+                        if (c < p.C) row[c] = p.normalize ? __fmul_rn(f[j], wn) : f[j];
+                    }
+                }
+                if (lane >= k && lane < k + nb) {
+                    float *row = stage + hw4 + (srows + lane - k) * cols;
+                    row[0] = pos[0];
+                    row[1] = pos[1];
+                    row[2] = pos[2];
+                    if (!p.normalize) row[3] = wraw;
+                }
+                srows += nb;
+                rows_done += nb;
+                k += nb;
+                if (srows == rows_per_stage) flush();
+            }
+        }
+    }
+    if (srows > 0) flush();
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 template <bool SCATTER>
 static cudaError_t launch_fill(FillParams &p, int dtype, const void *const *view_ptrs_host, int V_total,
                                cudaStream_t stream) {
@@ -878,19 +1026,39 @@ static cudaError_t launch_fill(FillParams &p, int dtype, const void *const *view
                          cols * 4 <= kStageBytes - 16 &&
                          reinterpret_cast<uintptr_t>(p.rows) % 4 == 0;
         if (tma) {
-            const size_t smem = (size_t)(kRayThreads / kWarp) * kStageBytes;
-            static thread_local int attr_dev[8] = {-1, -1, -1, -1, -1, -1, -1, -1};   // dynamic-smem opt-in, once per device
+            size_t smem = (size_t)(kRayThreads / kWarp) * kStageBytes;
+            static thread_local int attr_dev[16] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};   // dynamic-smem opt-in, once per device
             int dev = 0;
             cudaGetDevice(&dev);
             const int nj = (p.C + 31) / 32;
             auto go = [&](auto kernel, int slot) {
                 if (attr_dev[slot] != dev) {
-                    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kRayThreads / kWarp) * kStageBytes));
                     attr_dev[slot] = dev;
                 }
                 kernel<<<blocks, kRayThreads, smem, stream>>>(p);
             };
-            if (dtype == CNRMA_BF16) {
+            // short rows: per-ray work dominates -> the packed kernel (CNRMA_FILL_KERNEL=tma|packed overrides)
+            bool packed = cols * 4 <= kPackedRowBytesMax;
+            if (const char *env = std::getenv("CNRMA_FILL_KERNEL")) packed = (env[0] == 'p') && cols * 4 <= kHalfStageBytes - 16;
+            if (packed) {
+                // small staging halves for short rows: more resident CTAs (the kernel is latency-bound there)
+                // (measured: 2 KB halves beat 4 KB ones on 140-, 268- and 524-byte rows alike; 1 KB ones lose)
+                p.stage_half = (cols * 4 <= 2048 - 16) ? 2048 : kHalfStageBytes;
+                if (const char *env = std::getenv("CNRMA_FILL_STAGE_HALF")) p.stage_half = std::atoi(env);
+                smem = (size_t)(kRayThreads / kWarp) * 2 * p.stage_half;
+                if (dtype == CNRMA_BF16) {
+                    if (nj <= 1) go(fill_rows_packed_kernel<__nv_bfloat16, 1>, 8);
+                    else if (nj <= 2) go(fill_rows_packed_kernel<__nv_bfloat16, 2>, 9);
+                    else if (nj <= 4) go(fill_rows_packed_kernel<__nv_bfloat16, 4>, 10);
+                    else go(fill_rows_packed_kernel<__nv_bfloat16, 8>, 11);
+                } else {
+                    if (nj <= 1) go(fill_rows_packed_kernel<float, 1>, 12);
+                    else if (nj <= 2) go(fill_rows_packed_kernel<float, 2>, 13);
+                    else if (nj <= 4) go(fill_rows_packed_kernel<float, 4>, 14);
+                    else go(fill_rows_packed_kernel<float, 8>, 15);
+                }
+            } else if (dtype == CNRMA_BF16) {
                 if (nj <= 1) go(fill_rows_tma_kernel<__nv_bfloat16, 1>, 0);
                 else if (nj <= 2) go(fill_rows_tma_kernel<__nv_bfloat16, 2>, 1);
                 else if (nj <= 4) go(fill_rows_tma_kernel<__nv_bfloat16, 4>, 2);
