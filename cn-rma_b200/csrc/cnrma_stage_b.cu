@@ -535,17 +535,31 @@ __global__ void __launch_bounds__(kRayThreads) fill_rows_kernel(const __grid_con
     const float mean = (p.normalize && !SCATTER) ? __ldg(p.mean) : 1.0f;
     const int col0 = SCATTER ? 0 : (p.normalize ? 3 : 4);
 
+    // lane <-> ray: the ray of my pixel and the address of its feature vector, shuffled to the warp when the ray's turn
+    // comes (evaluating them warp-wide per ray costs 32x the instructions; with a hand-off selection most rays keep
+    // little or nothing and that setup was the bulk of the kernel)
+    float mo[3] = {0.0f, 0.0f, 0.0f}, md[3] = {0.0f, 0.0f, 0.0f};
+    const T *my_feat = nullptr;
+    if (my_cnt > 0) {
+        const int view = (int)(my_ray / hw);
+        const int pix = (int)(my_ray % hw);
+        const int u = pix % p.W, v = pix / p.W;
+        ray_of_pixel(p.pinv + 16 * view, u, v, mo, md);
+        my_feat = static_cast<const T *>(p.views[view - p.view_base]) + (int64_t)v * p.stride_y + (int64_t)u * p.stride_x;
+    }
+
     for (int r = 0; r < 32; ++r) {
         const int cnt = __shfl_sync(0xffffffffu, my_cnt, r);
         if (cnt == 0) continue;
         const int64_t off = __shfl_sync(0xffffffffu, my_off, r);
         const int64_t ray = ray0 + warp * 32 + r;
-        const int view = (int)(ray / hw);
-        const int pix = (int)(ray % hw);
-        const int u = pix % p.W, v = pix / p.W;
         float o[3], d[3];
-        ray_of_pixel(p.pinv + 16 * view, u, v, o, d);
-        const T *feat = static_cast<const T *>(p.views[view - p.view_base]) + (int64_t)v * p.stride_y + (int64_t)u * p.stride_x;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            o[a] = __shfl_sync(0xffffffffu, mo[a], r);
+            d[a] = __shfl_sync(0xffffffffu, md[a], r);
+        }
+        const T *feat = reinterpret_cast<const T *>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(my_feat), r));
         // records in chunks of 32: lane k prepares record k0 + k (position, scaled weight, target voxel) and writes
         // the row's leading columns; the feature columns are then streamed row by row with the weight broadcast
         for (int k0 = 0; k0 < cnt; k0 += 32) {
