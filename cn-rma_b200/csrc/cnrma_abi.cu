@@ -158,16 +158,10 @@ int cnrma_to_channels_last(const cnrma_features *src, void *dst, void *stream) {
     if (!dst) return CNRMA_ERR_ARG;
     const int d = device_ok();
     if (d != CNRMA_OK) return d;
-    const size_t esz = (src->dtype == CNRMA_BF16) ? 2 : 4;
-    const size_t per_view = (size_t)src->height * src->width * src->channels * esz;
-    for (int v = 0; v < src->views; ++v) {
-        const cudaError_t e = run_to_channels_last(src->view_ptrs_host[v], src->dtype, src->channels, src->height,
-                                                   src->width, src->stride_c, src->stride_y, src->stride_x,
-                                                   static_cast<unsigned char *>(dst) + (size_t)v * per_view,
-                                                   static_cast<cudaStream_t>(stream));
-        if (e != cudaSuccess) return fail_cuda(e);
-    }
-    return CNRMA_OK;
+    const cudaError_t e = run_to_channels_last(src->view_ptrs_host, src->views, src->dtype, src->channels, src->height,
+                                               src->width, src->stride_c, src->stride_y, src->stride_x, dst,
+                                               static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
 }
 
 float cnrma_t_one(const cnrma_grid *grid, double voxel_size, int grids) {

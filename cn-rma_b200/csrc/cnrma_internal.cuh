@@ -29,8 +29,8 @@ cudaError_t run_aggregate_bilinear(const GridDev &g, const cnrma_features &f, co
                                    float stride, uint32_t flags, float *volume, int32_t *count, uint8_t *valid,
                                    cudaStream_t stream);
 cudaError_t run_selftest_count_division(int max_n, unsigned long long *mismatches, cudaStream_t stream);
-cudaError_t run_to_channels_last(const void *src, int dtype, int C, int H, int W, int64_t sc, int64_t sy, int64_t sx,
-                                 void *dst, cudaStream_t stream);
+cudaError_t run_to_channels_last(const void *const *views_host, int views, int dtype, int C, int H, int W, int64_t sc,
+                                 int64_t sy, int64_t sx, void *dst, cudaStream_t stream);
 
 // cnrma_stage_b.cu
 RmaWorkspace rma_workspace(int views, int height, int width, int grids, int mode, float threshold, int depth_points,

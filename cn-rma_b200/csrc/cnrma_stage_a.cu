@@ -388,39 +388,70 @@ cudaError_t run_project_views(const GridDev &g, const float *proj, int64_t proj_
 }
 
 // ---- NCHW -> channels-last ------------------------------------------------------------------------
-// 32 channels x 32 pixels per tile through shared memory: reads coalesced along the pixel axis of the
-// source planes, writes coalesced along the channel axis of the destination rows.
+// Reference-layout (NCHW) maps -> channels-last rows, all views of a stack in one launch: tiles of 32 channels x 64
+// pixels through shared memory, reads coalesced along the pixel axis of the source planes (eight loads in flight per
+// thread), writes coalesced along the channel axis of the destination rows.  Contiguous planes (the usual case) are
+// addressed linearly; other strides go through the division by W.
+struct ChannelsLastParams {
+    int C, H, W;
+    int64_t sc, sy, sx;
+    int linear;                 // sx == 1 && sy == W: pixel offset == pixel index
+    unsigned char *dst;
+    size_t per_view_bytes;
+    const void *views[kMaxViewsPerLaunch];
+};
+
 template <typename T>
-__global__ void __launch_bounds__(256) to_channels_last_kernel(const T *__restrict__ src, int C, int H, int W,
-                                                               int64_t sc, int64_t sy, int64_t sx,
-                                                               T *__restrict__ dst) {
-    __shared__ T tile[32][33];
-    const int hw = H * W;
-    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+__global__ void __launch_bounds__(256) to_channels_last_kernel(const __grid_constant__ ChannelsLastParams p) {
+    __shared__ T tile[32][65];
+    const int hw = p.H * p.W;
+    const int p0 = blockIdx.x * 64, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const T *__restrict__ src = static_cast<const T *>(p.views[blockIdx.z]);
+    T *__restrict__ dst = reinterpret_cast<T *>(p.dst + (size_t)blockIdx.z * p.per_view_bytes);
+    T v[4][2];
 #pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-        const int c = c0 + ty + i, pix = p0 + tx;
-        if (c < C && pix < hw) tile[ty + i][tx] = src[(int64_t)c * sc + (int64_t)(pix / W) * sy + (int64_t)(pix % W) * sx];
-    }
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = c0 + ty + 8 * i, pix = p0 + tx + 32 * h;
+            v[i][h] = T(0.0f);
+            if (c < p.C && pix < hw) {
+                const int64_t off = p.linear ? (int64_t)pix : ((int64_t)(pix / p.W) * p.sy + (int64_t)(pix % p.W) * p.sx);
+                v[i][h] = src[(int64_t)c * p.sc + off];
+            }
+        }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) tile[ty + 8 * i][tx + 32 * h] = v[i][h];
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-        const int pix = p0 + ty + i, c = c0 + tx;
-        if (c < C && pix < hw) dst[(int64_t)pix * C + c] = tile[tx][ty + i];
+    for (int i = 0; i < 8; ++i) {
+        const int pix = p0 + ty + 8 * i, c = c0 + tx;
+        if (c < p.C && pix < hw) dst[(int64_t)pix * p.C + c] = tile[tx][ty + 8 * i];
     }
 }
 
-cudaError_t run_to_channels_last(const void *src, int dtype, int C, int H, int W, int64_t sc, int64_t sy, int64_t sx,
-                                 void *dst, cudaStream_t stream) {
-    const dim3 grid((H * W + 31) / 32, (C + 31) / 32);
-    if (dtype == CNRMA_BF16)
-        to_channels_last_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(src), C, H, W,
-                                                                        sc, sy, sx, static_cast<__nv_bfloat16 *>(dst));
-    else
-        to_channels_last_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float *>(src), C, H, W, sc, sy, sx,
-                                                                static_cast<float *>(dst));
-    return cudaGetLastError();
+// src: `views` maps with common strides (host array of device pointers) -> dst [views, H, W, C] contiguous.
+cudaError_t run_to_channels_last(const void *const *views_host, int views, int dtype, int C, int H, int W, int64_t sc,
+                                 int64_t sy, int64_t sx, void *dst, cudaStream_t stream) {
+    ChannelsLastParams p;
+    p.C = C; p.H = H; p.W = W;
+    p.sc = sc; p.sy = sy; p.sx = sx;
+    p.linear = (sx == 1 && sy == W);
+    p.per_view_bytes = (size_t)H * W * C * (dtype == CNRMA_BF16 ? 2 : 4);
+    for (int v0 = 0; v0 < views; v0 += kMaxViewsPerLaunch) {
+        const int nv = (views - v0 < kMaxViewsPerLaunch) ? (views - v0) : kMaxViewsPerLaunch;
+        for (int i = 0; i < nv; ++i) p.views[i] = views_host[v0 + i];
+        p.dst = static_cast<unsigned char *>(dst) + (size_t)v0 * p.per_view_bytes;
+        const dim3 grid((H * W + 63) / 64, (C + 31) / 32, nv);
+        if (dtype == CNRMA_BF16) to_channels_last_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(p);
+        else to_channels_last_kernel<float><<<grid, 256, 0, stream>>>(p);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 }  // namespace cnrma

@@ -83,16 +83,22 @@ class _FeatureStack:
 
     def _to_channels_last(self):
         lib = _lib.load()
-        out = torch.empty((self.V, self.B, self.H, self.W, self.C), dtype=self.dtype, device=self.device)
+        out = torch.empty((self.B, self.V, self.H, self.W, self.C), dtype=self.dtype, device=self.device)
+        # runs of consecutive views that share strides go out in one launch per batch element
+        runs, start = [], 0
+        for v in range(1, self.V + 1):
+            if v == self.V or self.views[v].stride() != self.views[start].stride():
+                runs.append((start, v))
+                start = v
         for b in range(self.B):
-            for v, f in enumerate(self.views):   # one launch per map: strides may differ between views
-                ptrs = (C.c_void_p * 1)(f[b].data_ptr())
-                sc, sy, sx = f.stride()[1:]
-                desc = _lib.Features(1, self.C, self.H, self.W, _DTYPES[self.dtype], sc, sy, sx,
+            for v0, v1 in runs:
+                sc, sy, sx = self.views[v0].stride()[1:]
+                ptrs = (C.c_void_p * (v1 - v0))(*[self.views[v][b].data_ptr() for v in range(v0, v1)])
+                desc = _lib.Features(v1 - v0, self.C, self.H, self.W, _DTYPES[self.dtype], sc, sy, sx,
                                      C.cast(ptrs, C.POINTER(C.c_void_p)))
-                _lib.check(lib.cnrma_to_channels_last(C.byref(desc), C.c_void_p(out[v, b].data_ptr()),
+                _lib.check(lib.cnrma_to_channels_last(C.byref(desc), C.c_void_p(out[b, v0].data_ptr()),
                                                       _stream(self.device)), "cnrma_to_channels_last")
-        return [out[v].permute(0, 3, 1, 2) for v in range(self.V)]
+        return [out[:, v].permute(0, 3, 1, 2) for v in range(self.V)]
 
     def descriptor(self, b, v0=0, nv=None):
         nv = self.V - v0 if nv is None else nv
