@@ -162,3 +162,22 @@ def make_grid(voxel_dim, voxel_size, origin):
     g.voxel_size = float(voxel_size)
     g.origin[0], g.origin[1], g.origin[2] = (float(v) for v in origin)
     return g
+
+
+def empty(*size, **kw):
+    """torch.empty for device outputs and scratch.  With CNRMA_POISON_OUTPUTS set (test aid) the buffer is filled with
+    0xFF bytes first -- NaN for floats, -1 for integers -- so that an element a kernel fails to write cannot hide
+    behind stale but plausible data left in a recycled allocator block (tests/test_gpu_poison.py)."""
+    import torch
+    t = torch.empty(*size, **kw)
+    if os.environ.get("CNRMA_POISON_OUTPUTS") and t.is_cuda and t.numel() > 0:
+        t.view(torch.uint8).fill_(0xFF)
+    return t
+
+
+def empty_like(x):
+    import torch
+    t = torch.empty_like(x)
+    if os.environ.get("CNRMA_POISON_OUTPUTS") and t.is_cuda and t.numel() > 0:
+        t.fill_(float("nan") if t.is_floating_point() else -1)
+    return t

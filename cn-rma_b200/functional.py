@@ -83,7 +83,7 @@ class _FeatureStack:
 
     def _to_channels_last(self):
         lib = _lib.load()
-        out = torch.empty((self.B, self.V, self.H, self.W, self.C), dtype=self.dtype, device=self.device)
+        out = _lib.empty((self.B, self.V, self.H, self.W, self.C), dtype=self.dtype, device=self.device)
         # runs of consecutive views that share strides go out in one launch per batch element
         runs, start = [], 0
         for v in range(1, self.V + 1):
@@ -231,9 +231,9 @@ def project_views(projections, voxel_dim, voxel_size, origin, stride, height, wi
     V, B = P.shape[:2]
     nvox = int(voxel_dim[0]) * int(voxel_dim[1]) * int(voxel_dim[2])
     grid = _lib.make_grid(voxel_dim, voxel_size, _origin3(origin))
-    px = torch.empty((B, V, nvox), dtype=torch.int32, device=device)
-    py = torch.empty_like(px)
-    valid = torch.empty((B, V, nvox), dtype=torch.bool, device=device)
+    px = _lib.empty((B, V, nvox), dtype=torch.int32, device=device)
+    py = _lib.empty_like(px)
+    valid = _lib.empty((B, V, nvox), dtype=torch.bool, device=device)
     with torch.cuda.device(device):
         for b in range(B):
             _lib.check(lib.cnrma_project_views(C.byref(grid), C.c_void_p(P[0, b].data_ptr()), B * 12, V,
@@ -264,9 +264,9 @@ def aggregate_views(projections, features, voxel_dim, voxel_size, origin, stride
     grid = _lib.make_grid(voxel_dim, voxel_size, _origin3(origin))
     flags = (_lib.AGG_MEAN if mean else 0) | (_lib.AGG_COUNT_F32 if count_f32 else 0)
     if out is None:
-        buf = torch.empty((fs.B, nx, ny, nz, fs.C), dtype=torch.float32, device=device)
-        count = torch.empty((fs.B, 1, nx, ny, nz), dtype=torch.float32 if count_f32 else torch.int32, device=device)
-        valid = torch.empty((fs.B, 1, nx, ny, nz), dtype=torch.bool, device=device)
+        buf = _lib.empty((fs.B, nx, ny, nz, fs.C), dtype=torch.float32, device=device)
+        count = _lib.empty((fs.B, 1, nx, ny, nz), dtype=torch.float32 if count_f32 else torch.int32, device=device)
+        valid = _lib.empty((fs.B, 1, nx, ny, nz), dtype=torch.bool, device=device)
         volume = buf.permute(0, 4, 1, 2, 3)
     else:
         volume, count, valid = out
@@ -304,9 +304,9 @@ def aggregate_views_bilinear(projections, features, voxel_dim, voxel_size, origi
     P = _projections_device(projections, device)
     nx, ny, nz = (int(v) for v in voxel_dim)
     grid = _lib.make_grid(voxel_dim, voxel_size, _origin3(origin))
-    buf = torch.empty((fs.B, nx, ny, nz, fs.C), dtype=torch.float32, device=device)
-    count = torch.empty((fs.B, 1, nx, ny, nz), dtype=torch.int32, device=device)
-    valid = torch.empty((fs.B, 1, nx, ny, nz), dtype=torch.bool, device=device)
+    buf = _lib.empty((fs.B, nx, ny, nz, fs.C), dtype=torch.float32, device=device)
+    count = _lib.empty((fs.B, 1, nx, ny, nz), dtype=torch.int32, device=device)
+    valid = _lib.empty((fs.B, 1, nx, ny, nz), dtype=torch.bool, device=device)
     with torch.cuda.device(device):
         for b in range(fs.B):
             desc = fs.descriptor(b)
@@ -405,8 +405,8 @@ def get_ray_parameter(projection, features):
     device = features.device
     B, _c, H, W = features.shape
     pinv = invert_projections(projection).to(device)
-    o = torch.empty((B, 3, H * W), dtype=torch.float32, device=device)
-    d = torch.empty_like(o)
+    o = _lib.empty((B, 3, H * W), dtype=torch.float32, device=device)
+    d = _lib.empty_like(o)
     with torch.cuda.device(device):
         _lib.check(lib.cnrma_ray_parameters(C.c_void_p(pinv.data_ptr()), B, H, W, C.c_void_p(o.data_ptr()),
                                             C.c_void_p(d.data_ptr()), _stream(device)), "cnrma_ray_parameters")
@@ -437,8 +437,8 @@ def _march(fs, b, P_scaled_b, tsdf_b, grid, voxel_dim, voxel_size, grids, mode, 
     nbytes = C.c_size_t(0)
     _lib.check(lib.cnrma_rma_workspace_bytes(C.byref(grid), fs.V, fs.H, fs.W, m.grids, m.mode, m.threshold, m.depth_points,
                                              C.byref(nbytes)), "cnrma_rma_workspace_bytes")
-    m.workspace = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
-    m.result = torch.empty(C.sizeof(_lib.RmaResult), dtype=torch.uint8, device=device)
+    m.workspace = _lib.empty(nbytes.value, dtype=torch.uint8, device=device)
+    m.result = _lib.empty(C.sizeof(_lib.RmaResult), dtype=torch.uint8, device=device)
     if tsdf_b.dtype != torch.float32 or not tsdf_b.is_contiguous() or tsdf_b.device != device:
         tsdf_b = tsdf_b.detach().to(device=device, dtype=torch.float32).contiguous()
     if tuple(tsdf_b.shape) != tuple(int(v) for v in voxel_dim):
@@ -486,7 +486,7 @@ def _fill(fs, b, m, grid, rows_host, normalize, mean_tensor=None, desc=None, cap
     device = fs.device
     cols = fs.C + (3 if normalize else 4)
     cap = rows_host if capacity is None else capacity
-    rows = torch.empty((cap, cols), dtype=torch.float32, device=device)
+    rows = _lib.empty((cap, cols), dtype=torch.float32, device=device)
     if cap == 0:
         return rows
     desc = desc if desc is not None else fs.descriptor(b)
@@ -595,8 +595,8 @@ def rma_dense_weights(projections, height, width, tsdf, voxel_dim, voxel_size, o
     with torch.cuda.device(device):
         m = _march(fs, 0, P_scaled[:, 0], tsdf[0, 0], grid, voxel_dim, voxel_size, grids, "neus", threshold, None)
         n = fs.V * fs.H * fs.W * int(grids)
-        w = torch.empty(n, dtype=torch.float32, device=device)
-        keep = torch.empty(n, dtype=torch.bool, device=device)
+        w = _lib.empty(n, dtype=torch.float32, device=device)
+        keep = _lib.empty(n, dtype=torch.bool, device=device)
         _lib.check(lib.cnrma_rma_expand(fs.V, fs.H, fs.W, int(grids), float(threshold),
                                         C.c_void_p(m.workspace.data_ptr()), C.c_void_p(w.data_ptr()),
                                         C.c_void_p(keep.data_ptr()), _stream(device)), "cnrma_rma_expand")
@@ -667,10 +667,10 @@ def sample_points_device(n, max_points, seed, device):
     use sample_points for parity).  Avoids the host-side permutation of n indices (~0.2 s for 6 M points)."""
     lib = _lib.load()
     device = torch.device(device)
-    mask = torch.empty(n, dtype=torch.bool, device=device)
+    mask = _lib.empty(n, dtype=torch.bool, device=device)
     nbytes = C.c_size_t(0)
     _lib.check(lib.cnrma_sample_workspace_bytes(C.byref(nbytes)), "cnrma_sample_workspace_bytes")
-    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
+    ws = _lib.empty(nbytes.value, dtype=torch.uint8, device=device)
     with torch.cuda.device(device):
         _lib.check(lib.cnrma_sample_mask(n, int(max_points), int(seed) & 0xFFFFFFFFFFFFFFFF, C.c_void_p(ws.data_ptr()),
                                          nbytes.value, C.c_void_p(mask.data_ptr()), _stream(device)), "cnrma_sample_mask")
@@ -683,9 +683,9 @@ def _mask_prefix(mask_dev):
     n = mask_dev.numel()
     nbytes = C.c_size_t(0)
     _lib.check(lib.cnrma_handoff_workspace_bytes(n, C.byref(nbytes)), "cnrma_handoff_workspace_bytes")
-    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
-    prefix = torch.empty(n, dtype=torch.int32, device=device)
-    kept = torch.empty(1, dtype=torch.int64, device=device)
+    ws = _lib.empty(nbytes.value, dtype=torch.uint8, device=device)
+    prefix = _lib.empty(n, dtype=torch.int32, device=device)
+    kept = _lib.empty(1, dtype=torch.int64, device=device)
     _lib.check(lib.cnrma_mask_prefix(C.c_void_p(mask_dev.data_ptr()), n, C.c_void_p(ws.data_ptr()), nbytes.value,
                                      C.c_void_p(prefix.data_ptr()), C.c_void_p(kept.data_ptr()), _stream(device)),
                "cnrma_mask_prefix")
@@ -723,7 +723,7 @@ def switch_pointcloud(points, offsets, max_points=None, masks=None, rng=None):
         else:
             n_sel = int(mask.sum())
             mask_dev = _to_mask_dev(mask, n, device)
-        out = torch.empty((n_sel, cols), dtype=torch.float32, device=device)
+        out = _lib.empty((n_sel, cols), dtype=torch.float32, device=device)
         if n_sel > 0:
             with torch.cuda.device(device):
                 prefix, _kept = _mask_prefix(mask_dev)
@@ -772,7 +772,7 @@ def rma_points_selected(projections, features, tsdf, voxel_dim, voxel_size, orig
                 n_sel = int(mask.sum())
                 mask_dev = _to_mask_dev(mask, n, device)
             cols = fs.C + 3
-            out = torch.empty((n_sel, cols), dtype=torch.float32, device=device)
+            out = _lib.empty((n_sel, cols), dtype=torch.float32, device=device)
             if n_sel > 0:
                 prefix, _kept = _mask_prefix(mask_dev)
                 off3 = (C.c_float * 3)(*_origin3(offsets[b]))

@@ -54,8 +54,8 @@ def _scale_forward(x, weight, prev, label_smoothing, sparse_threshold, want_mask
         prev = prev.detach().to(device=x.device, dtype=torch.float32).contiguous()
         if tuple(prev.shape) != (B, 1, nx // 2, ny // 2, nz // 2) or (nx | ny | nz) & 1:
             raise ValueError(f"previous scale {tuple(prev.shape)} is not half of {tuple(x.shape)}")
-    tsdf = torch.empty((B, 1, nx, ny, nz), dtype=torch.float32, device=x.device)
-    mask = torch.empty((B, 1, nx, ny, nz), dtype=torch.bool, device=x.device) if want_mask else None
+    tsdf = _lib.empty((B, 1, nx, ny, nz), dtype=torch.float32, device=x.device)
+    mask = _lib.empty((B, 1, nx, ny, nz), dtype=torch.bool, device=x.device) if want_mask else None
     with torch.cuda.device(x.device):
         for b in range(B):
             sc, sv = _strides(x[b])
@@ -87,12 +87,12 @@ class _HeadScale(torch.autograd.Function):
         B, Cc, nx, ny, nz = x.shape
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         g = grad_tsdf.detach().to(torch.float32).contiguous()
-        grad_x = torch.empty_like(x) if need_x else None           # same strides as x
+        grad_x = _lib.empty_like(x) if need_x else None           # same strides as x
         grad_w = torch.zeros(Cc, dtype=torch.float32, device=x.device) if need_w else None
-        gw_b = torch.empty(Cc, dtype=torch.float32, device=x.device) if need_w else None
+        gw_b = _lib.empty(Cc, dtype=torch.float32, device=x.device) if need_w else None
         ws = None
         if need_w:
-            ws = torch.empty(int(lib.cnrma_tsdf_head_workspace_bytes(Cc)), dtype=torch.uint8, device=x.device)
+            ws = _lib.empty(int(lib.cnrma_tsdf_head_workspace_bytes(Cc)), dtype=torch.uint8, device=x.device)
         with torch.cuda.device(x.device):
             for b in range(B):
                 sc, sv = _strides(x[b])
