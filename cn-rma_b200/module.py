@@ -151,3 +151,31 @@ def make_detector_class(ray_marching_cls):
         valid = property(RayMarchingAggregator.valid.fget, lambda self, v: None)
 
     return RayMarchingB200
+
+
+def make_atlas_class(atlas_cls):
+    """The same adapter for the reconstruction-only model `Atlas` (projects/mvsdetection/models/atlas.py:71-...,
+    "at.py"), whose `inference1` / `inference2` carry a copy of Stage A (at.py:20-67 `backproject`, :118-179):
+    `AtlasB200 = make_atlas_class(Atlas)`.  `inference1` records its (projection, feature) pair (running the 2D
+    backbone first when an image is passed, at.py:141-143); `inference2` runs the fused Stage A kernel over all recorded
+    views, mean and NaN scrub included (at.py:167-172), then the 3D networks as in the reference (at.py:174-176)."""
+
+    class AtlasB200(atlas_cls):
+        initialize_volume = RayMarchingAggregator.initialize_volume
+        _flush = RayMarchingAggregator._flush
+        clear_3d_features = RayMarchingAggregator.clear_3d_features
+        volume = property(RayMarchingAggregator.volume.fget, lambda self, v: None)
+        valid = property(RayMarchingAggregator.valid.fget, lambda self, v: None)
+
+        def inference1(self, projection, image=None, feature=None):
+            assert ((image is not None and feature is None) or (image is None and feature is not None))
+            if feature is None:
+                feature = self.backbone2d(self.normalizer(image))
+            RayMarchingAggregator.aggregate_2d_features(self, projection, feature)
+
+        def inference2(self, targets=None):
+            self.clear_3d_features()
+            x = self.backbone3d(self.volume)
+            return self.tsdf_head(x, targets)
+
+    return AtlasB200

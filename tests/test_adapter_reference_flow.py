@@ -140,3 +140,42 @@ def test_reference_control_flow_on_adapter_class(monkeypatch, tmp_path, flow, ma
     assert float(ref_l["det_rows"]) == float(my_l["det_rows"]) == (min(max_points, ref_pts[0].shape[0]) if max_points
                                                                    else ref_pts[0].shape[0])
     assert abs(float(ref_l["det_loss"]) - float(my_l["det_loss"])) <= 1e-5 * abs(float(ref_l["det_loss"]))
+
+
+@pytest.mark.parametrize("flow", ["forward_train", "forward_test"])
+def test_reference_atlas_flow_on_adapter_class(monkeypatch, tmp_path, flow):
+    """The reconstruction-only model (models/atlas.py): its own forward_train / forward_test on `make_atlas_class(Atlas)`
+    against the reference class -- same accumulated volume, same TSDF outputs."""
+    import importlib
+    import cnrma_b200
+    ref_shim.load_reference()
+    at = importlib.import_module("projects.mvsdetection.models.atlas")
+    head_mod = importlib.import_module("projects.mvsdetection.models.atlas_head")
+    _standins(monkeypatch)
+    Adapter = cnrma_b200.make_atlas_class(at.Atlas)
+    assert Adapter.forward_train is at.Atlas.forward_train and Adapter.forward_test is at.Atlas.forward_test
+    inputs = _inputs()
+    outs = []
+    for cls in (at.Atlas, Adapter):
+        torch.manual_seed(3)
+        m = cls(pixel_mean=[0.0, 0.0, 0.0], pixel_std=[1.0, 1.0, 1.0], voxel_size=VOXEL_SIZE, n_scales=3,
+                voxel_dim_train=VOXEL_DIM, voxel_dim_test=VOXEL_DIM, origin=[0, 0, 0], backbone2d_stride=STRIDE,
+                backbone2d={}, feature_2d={}, backbone_3d={}, tsdf_head={}, save_path=str(tmp_path))
+        conv = torch.nn.Conv2d(3, C_FEAT, 3, padding=1)
+        m.fpn = lambda img, conv=conv: torch.nn.functional.avg_pool2d(conv(img), STRIDE)
+        m.feature_2d = lambda x: x
+        pool = torch.nn.functional.avg_pool3d
+        m.backbone3d = lambda vol: [pool(vol, 4).repeat(1, 2, 1, 1, 1), pool(vol, 2), vol[:, :4]]
+        m.tsdf_head = head_mod.AtlasTSDFHead([4, C_FEAT, 2 * C_FEAT], 3, 0.04, 1.05, [0.99, 0.99, 0.99])
+        for d in m.tsdf_head.decoders:
+            torch.nn.init.normal_(d.weight, std=2.0)
+        captured = {}
+        m.tsdf_head.register_forward_hook(lambda _mod, _inp, out, _cap=captured: _cap.update(out[0]))
+        m.post_process = lambda *a, **k: []
+        with torch.no_grad():
+            getattr(m, flow)(inputs)
+        outs.append(captured)
+    ref_o, my_o = outs
+    assert set(ref_o) == set(my_o) == {"scene_tsdf_016", "scene_tsdf_008", "scene_tsdf_004"}
+    for k in ref_o:
+        assert torch.equal(ref_o[k], my_o[k]), k
