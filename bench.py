@@ -185,7 +185,10 @@ def run_reference_arm(args):
     oracle.build()
     cores = oracle.num_threads()
     sc = synthetic.make_scene(args.config, seed=0, with_features=False)
-    views = cpu_sample_views(oracle, sc, args.threshold, 2.0, args.cpu_views)     # ~2 s of CPU work per step
+    # bounded sample per step: ~2 s of CPU work, less when many steps are requested, so that the whole run stays
+    # within a few minutes whatever --steps says
+    per_step_s = max(0.05, min(2.0, 150.0 / max(args.steps + min(args.warmup, 2), 1)))
+    views = cpu_sample_views(oracle, sc, args.threshold, per_step_s, args.cpu_views)
     feats = cpu_features(sc, views)
     for _ in range(min(args.warmup, 2)):
         cpu_step(oracle, sc, feats, views, args.threshold)
