@@ -494,3 +494,23 @@ def test_many_views_short_rows_batches(cn, views, channels, dtype):
         assert np.array_equal(vol[0].cpu().numpy().view(np.uint32), ovol.view(np.uint32)), kernel
         results.append(vol)
     assert int(ocnt.max()) > 8
+
+
+@pytest.mark.parametrize("channels", [8, 256])
+def test_speculative_fill_with_wrong_row_hint(cn, channels):
+    """rma_points launches the fill before M is read back, into a buffer sized from the previous call with the same
+    shapes (functional._rows_hint).  A hint that is too small makes the kernel drop the rows beyond the capacity and
+    the host refill; a hint that is too large just leaves slack.  Both must give the rows of a first call -- for the
+    packed (short rows) and the TMA-store (long rows) fill kernels."""
+    import cnrma_b200.functional as F
+    sc = cn.synthetic.make_scene("small", seed=4, channels=channels)
+    p, f, t = _scene_tensors(sc)
+    args = (sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
+    F._rows_hint.clear()
+    first = cn.rma_points(p, f, t, *args, grids=sc.grids, threshold=0.05)[0].clone()     # no hint: M read first
+    assert len(F._rows_hint) == 1 and first.shape[0] > 2000
+    key = next(iter(F._rows_hint))
+    for hint in (1, 777, first.shape[0] - 1, first.shape[0], 3 * first.shape[0]):
+        F._rows_hint[key] = hint
+        again = cn.rma_points(p, f, t, *args, grids=sc.grids, threshold=0.05)[0]
+        assert again.shape == first.shape and torch.equal(again, first), hint
