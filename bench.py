@@ -408,6 +408,8 @@ def main():
                    "host_cpus": numa},
         "scenes_per_s": world / (ms_step * 1e-3),
         "ray_steps_per_s": world * sc.ray_steps / (ms_step * 1e-3),
+        # the dense (Stage A) lift alone, the quantity SURVEY.md section 8d's 60 % target is stated on
+        "stage_a_voxel_views_per_s": (world * sc.voxel_views / (ms_a * 1e-3)) if ms_a else None,
         "stage_ms": {"stage_a": ms_a, "march": ms_march, "fill": ms_fill},
         "kernels": kernels, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
         "handoff": handoff,
