@@ -27,6 +27,7 @@ struct AggBwdParams {
     const int32_t *count;
     uint32_t flags;               // CNRMA_AGG_MEAN: the forward divided by the count
     int chunk_floats;             // floats of a row handled per pass (<= 256)
+    SweepOrder sweep;             // same traversal order as the forward kernel
     float *views[kMaxViewsPerLaunch];
 };
 
@@ -56,14 +57,11 @@ __global__ void __launch_bounds__(kAggThreads, 4) aggregate_views_backward_kerne
     for (int i = threadIdx.x; i < p.V; i += blockDim.x) sView[i] = p.views[i];
     __syncthreads();
 
-    const int nxy = p.g.nx * p.g.ny;
-    const float inv_nxy = 1.0f / (float)nxy, inv_ny = 1.0f / (float)p.g.ny;
     const int warps_total = gridDim.x * kWarps;
     const int chunks = (p.C + p.chunk_floats - 1) / p.chunk_floats;
     for (int it = blockIdx.x * kWarps + warp; it < p.nvox; it += warps_total) {
-        int vz, rem, vx, vy;
-        fast_divmod(it, nxy, inv_nxy, vz, rem);
-        fast_divmod(rem, p.g.ny, inv_ny, vx, vy);
+        int vx, vy, vz;
+        sweep_voxel(p.sweep, it, vx, vy, vz);
         const int vox = (vx * p.g.ny + vy) * p.g.nz + vz;
         const int cnt = __ldg(p.count + vox);
         if (cnt == 0) continue;   // no view sees the voxel: its gradient goes nowhere
@@ -115,6 +113,7 @@ cudaError_t run_aggregate_views_backward(const GridDev &g, const cnrma_features 
     p.count = count;
     p.flags = flags;
     p.chunk_floats = gf.channels < 256 ? gf.channels : 256;
+    p.sweep = make_sweep(g.nx, g.ny, g.nz, sweep_thickness(g.ny, g.nz, gf.views, gf.channels * 4));
     static thread_local int ctas = 0, ctas_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);

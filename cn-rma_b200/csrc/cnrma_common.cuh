@@ -5,6 +5,9 @@
 // choices; the library is additionally compiled with --fmad=false.
 #pragma once
 
+#include <cmath>
+#include <cstdlib>
+
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -187,6 +190,51 @@ __device__ __forceinline__ void fast_divmod(int n, int d, float inv_d, int &q, i
     r = n - q * d;
     if (r < 0) { r += d; --q; }
     else if (r >= d) { r -= d; ++q; }
+}
+
+// Traversal order of the Stage A kernels (forward and backward): the volume is swept in slabs of T z-slices, inside a
+// slab x is the slow axis, then y, then the slab's z.  Voxels that share a pixel row lie along one camera ray, 8+
+// voxels apart and a few slices up or down; what the resident warps touch at any time is a window of a few thousand
+// voxels (L2 size / bytes gathered per voxel), and a window of ~T x-rows by all y by T slices keeps more of those
+// pairs together than one of whole z-slices (T = 1) or whole columns (T = nz).  LRU simulation and measurement in
+// DESIGN.md "K_A".  T is chosen on the host: sweep_thickness().
+struct SweepOrder {
+    int ny, T, Tlast, nfull, full;   // full = nx*ny*T voxels per full slab, nfull full slabs, then one of Tlast slices
+    float inv_full, inv_T, inv_Tlast, inv_ny;
+};
+
+inline SweepOrder make_sweep(int nx, int ny, int nz, int T) {
+    SweepOrder s;
+    s.ny = ny;
+    s.T = T < 1 ? 1 : (T > nz ? nz : T);
+    s.nfull = nz / s.T;
+    s.Tlast = nz - s.nfull * s.T;
+    if (s.Tlast == 0) s.Tlast = s.T;   // unused then; keeps the reciprocal finite
+    s.full = nx * ny * s.T;
+    s.inv_full = 1.0f / (float)s.full;
+    s.inv_T = 1.0f / (float)s.T;
+    s.inv_Tlast = 1.0f / (float)s.Tlast;
+    s.inv_ny = 1.0f / (float)ny;
+    return s;
+}
+
+// Slab thickness: the window holds about L2_window / (visible views x row bytes) voxels; make it as deep in z as it is
+// long in x (it always spans y): T = sqrt(window_voxels / ny).  A quarter of the views see a voxel in the scenes at hand.
+inline int sweep_thickness(int ny, int nz, int views, int row_bytes) {
+    if (const char *env = std::getenv("CNRMA_AGG_SLAB")) return std::atoi(env);   // tuning aid
+    const double per_voxel = 0.25 * (views > 0 ? views : 1) * (row_bytes > 0 ? row_bytes : 1);
+    const double window_voxels = 64.0 * 1024 * 1024 / per_voxel;
+    int T = (int)(std::sqrt(window_voxels / (ny > 0 ? ny : 1)) + 0.5);
+    return T < 1 ? 1 : (T > nz ? nz : T);
+}
+
+__device__ __forceinline__ void sweep_voxel(const SweepOrder &s, int it, int &vx, int &vy, int &vz) {
+    int slab, rem, xy, zi;
+    fast_divmod(it, s.full, s.inv_full, slab, rem);
+    const bool last = slab >= s.nfull;
+    fast_divmod(rem, last ? s.Tlast : s.T, last ? s.inv_Tlast : s.inv_T, xy, zi);
+    vz = slab * s.T + zi;
+    fast_divmod(xy, s.ny, s.inv_ny, vx, vy);
 }
 
 // IEEE-correct a / n for a small positive integer n, given y = RN(1/n): q = RN(a*y); r = a - n*q (exact, FMA);

@@ -43,6 +43,7 @@ struct AggParams {
     int write_count;              // this launch owns count/valid (see run_aggregate)
     int chunk_bytes;              // bytes of a feature row handled per pass (multiple of 16, <= kMaxChunkBytes)
     int rows_cap;                 // row slots per warp buffer
+    SweepOrder sweep;             // traversal order of the voxels
     const void *views[kMaxViewsPerLaunch];
 };
 
@@ -88,15 +89,11 @@ aggregate_views_kernel(const __grid_constant__ AggParams p) {
     uint32_t parity = 0;
 
     const int warps_total = gridDim.x * kWarps;
-    const int nxy = p.g.nx * p.g.ny;
-    const float inv_nxy = 1.0f / (float)nxy, inv_ny = 1.0f / (float)p.g.ny;
     for (int it = blockIdx.x * kWarps + warp; it < p.nvox; it += warps_total) {
-        // Traversal order: z-slices (all resident warps sweep the volume slice by slice).  Voxels that share a
-        // pixel lie along one camera ray, and rays of roughly level cameras stay within a few z-slices, so
-        // their repeated gathers of that pixel's row fall inside the L2 residency window (DESIGN.md "K_A").
-        int vz, rem, vx, vy;
-        fast_divmod(it, nxy, inv_nxy, vz, rem);
-        fast_divmod(rem, p.g.ny, inv_ny, vx, vy);
+        // Traversal order: slabs of a few z-slices (SweepOrder in cnrma_common.cuh): all resident warps sweep the
+        // volume together, and repeated gathers of a pixel's row fall inside the L2 residency window more often.
+        int vx, vy, vz;
+        sweep_voxel(p.sweep, it, vx, vy, vz);
         // voxel order of datasets/tsdf.py:24-29: flat = (x*ny + y)*nz + z
         const int vox = (vx * p.g.ny + vy) * p.g.nz + vz;
         const float wx = world_coord(vx, p.g.vs, p.g.ox);
@@ -315,6 +312,7 @@ cudaError_t run_aggregate_views(const GridDev &g, const cnrma_features &f, int v
     for (int i = 0; i < nv; ++i) p.views[i] = f.view_ptrs_host[v0 + i];
     p.chunk_bytes = 0;
     p.rows_cap = 0;
+    p.sweep = make_sweep(g.nx, g.ny, g.nz, sweep_thickness(g.ny, g.nz, nv, row_bytes));
     return run_aggregate(p, f.dtype, max_chunk_bytes, stream);
 }
 

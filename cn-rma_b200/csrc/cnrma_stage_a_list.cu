@@ -32,6 +32,7 @@ struct ListParams {
     int chunk_base, write_count;
     int nb;     // voxels per warp batch (<= 32)
     int lcap;   // list capacity per voxel (odd, >= V)
+    SweepOrder sweep;   // traversal order of the voxels (cnrma_common.cuh)
     // uniform: the views are equally spaced in one allocation, so a list entry is the row's offset from views[0] in
     // 16-byte units (one multiply-add to decode); otherwise entries pack (view, py, px) and go through the pointer table
     int uniform;
@@ -71,19 +72,16 @@ __global__ void __launch_bounds__(kListThreads) aggregate_views_list_kernel(cons
     const int grp = lane / G, lig = lane % G;
     const unsigned char *view0 = (p.V > 0) ? sView[0] : nullptr;
     const int c0 = chunk * (kChunkBytes / (int)sizeof(T)) + lig * E;   // first channel of this lane (+ q*G*E)
-    const int nxy = p.g.nx * p.g.ny;
-    const float inv_nxy = 1.0f / (float)nxy, inv_ny = 1.0f / (float)p.g.ny;
     const int units = (p.nvox + p.nb - 1) / p.nb;
     const int warps_total = gridDim.x * kWarps;
     const float fW = (float)p.W - 0.5f, fH = (float)p.H - 0.5f;
 
     for (int u = blockIdx.x * kWarps + warp; u < units; u += warps_total) {
         // ---- phase 1: lane <-> voxel -------------------------------------------------------------------------
-        const int it = u * p.nb + lane;                       // z-slice sweep index
+        const int it = u * p.nb + lane;                       // index in the sweep order
         const bool active = lane < p.nb && it < p.nvox;
-        int vz, rem, vx, vy;
-        fast_divmod(active ? it : 0, nxy, inv_nxy, vz, rem);
-        fast_divmod(rem, p.g.ny, inv_ny, vx, vy);
+        int vx, vy, vz;
+        sweep_voxel(p.sweep, active ? it : 0, vx, vy, vz);
         const int vox = (vx * p.g.ny + vy) * p.g.nz + vz;    // voxel order of datasets/tsdf.py:24-29
         const float wx = world_coord(vx, p.g.vs, p.g.ox);
         const float wy = world_coord(vy, p.g.vs, p.g.oy);
@@ -271,6 +269,7 @@ cudaError_t run_aggregate_list(const GridDev &g, const cnrma_features &f, int v0
     p.valid = valid;
     p.flags = flags;
     p.vec_store = (vsc == 1) && (vsv % 4 == 0) && (reinterpret_cast<uintptr_t>(volume) % 16 == 0);
+    p.sweep = make_sweep(g.nx, g.ny, g.nz, sweep_thickness(g.ny, g.nz, nv, f.channels * esz));
     p.lcap = nv | 1;                                      // odd: the lanes' list writes hit different banks
     int nb = 32;                                          // voxels per warp batch: lists must fit ~8 KB per warp
     while (nb > 1 && (size_t)nb * p.lcap * 4 > 8192) nb >>= 1;
