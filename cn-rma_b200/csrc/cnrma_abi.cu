@@ -138,8 +138,14 @@ int cnrma_aggregate_views_bilinear(const cnrma_grid *grid, const cnrma_features 
     if (features->views > kMaxViewsPerLaunch) return CNRMA_ERR_UNSUPPORTED;
     const int d = device_ok();
     if (d != CNRMA_OK) return d;
-    const cudaError_t e = run_aggregate_bilinear(to_dev(*grid), *features, projections, proj_view_stride, stride, flags,
-                                                 volume, count, valid, static_cast<cudaStream_t>(stream));
+    cudaError_t e;
+    if (std::getenv("CNRMA_BILINEAR_SIMPLE") != nullptr)   // the first, simple kernel (kept as a second opinion for the tests)
+        e = run_aggregate_bilinear(to_dev(*grid), *features, projections, proj_view_stride, stride, flags, volume, count,
+                                   valid, static_cast<cudaStream_t>(stream));
+    else
+        e = run_aggregate_views(to_dev(*grid), *features, 0, features->views, projections, proj_view_stride, stride,
+                                (flags & CNRMA_AGG_MEAN) | kAggBilinearInternal, volume, features->channels, 1, count, valid,
+                                0, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
 }
 

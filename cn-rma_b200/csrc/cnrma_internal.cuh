@@ -58,6 +58,7 @@ size_t sample_workspace_bytes();
 cudaError_t run_sample_mask(int64_t n, int64_t k, unsigned long long seed, void *workspace, uint8_t *mask,
                             cudaStream_t stream);
 
+constexpr uint32_t kAggBilinearInternal = 0x80000000u;   // library-internal flag bit: run_aggregate_views in bilinear mode
 constexpr int kListViewsMax = 96;     // the list kernel's per-voxel lists stop paying beyond this many views per launch
 constexpr int kListViewsBatch = 63;   // batch size used to split longer view lists (32 voxels x 63 entries fit a warp's 8 KB)
 

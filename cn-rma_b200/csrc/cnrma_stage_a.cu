@@ -44,6 +44,7 @@ struct AggParams {
     int chunk_bytes;              // bytes of a feature row handled per pass (multiple of 16, <= kMaxChunkBytes)
     int rows_cap;                 // row slots per warp buffer
     SweepOrder sweep;             // traversal order of the voxels
+    int bilinear;                 // opt-in variant: four neighbouring rows per visible view
     const void *views[kMaxViewsPerLaunch];
 };
 
@@ -51,8 +52,11 @@ constexpr int kMaxChunkBytes = 1024;     // 64 16-byte vectors: two per lane
 constexpr int kWarpBufferBytes = 6144;   // per-warp row buffer: 4 CTAs x 8 warps x 6 KB = 192 KB per SM
 constexpr int kAggCtasPerSm = 4;
 
-template <int VPL, typename T>
-__global__ void __launch_bounds__(kAggThreads, kAggCtasPerSm)
+// BILINEAR (opt-in variant, cnrma_aggregate_views_bilinear): every visible view contributes its four neighbouring pixel
+// rows -- four bulk copies into four consecutive slots, the interpolation weights beside them -- instead of the one
+// nearest row; the validity mask and the count are the nearest path's.
+template <int VPL, typename T, bool BILINEAR>
+__global__ void __launch_bounds__(kAggThreads, BILINEAR ? 2 : kAggCtasPerSm)
 aggregate_views_kernel(const __grid_constant__ AggParams p) {
     using V16 = Vec16<T>;
     constexpr int E = V16::kElems;   // channels per 16-byte vector
@@ -67,6 +71,7 @@ aggregate_views_kernel(const __grid_constant__ AggParams p) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     unsigned char *rowbuf = smem_raw + head + (size_t)warp * p.rows_cap * p.chunk_bytes;
+    float *wbuf = reinterpret_cast<float *>(smem_raw + head + (size_t)kWarps * p.rows_cap * p.chunk_bytes) + warp * p.rows_cap;   // BILINEAR: weight per slot
 
     for (int i = threadIdx.x; i < 12 * p.V; i += blockDim.x) {
         const int v = i / 12, k = i % 12;
@@ -125,13 +130,32 @@ aggregate_views_kernel(const __grid_constant__ AggParams p) {
             mbar_wait(bar, parity);
             parity ^= 1u;
             const unsigned char *row = rowbuf + (lane << 4);
-            for (int r = 0; r < filled; ++r, row += p.chunk_bytes) {
+            if (BILINEAR) {
+                __syncwarp();   // the weights were written by the issuing lanes
+                for (int r = 0; r < filled; r += 4, row += 4 * p.chunk_bytes) {
+                    const float w00 = wbuf[r], w10 = wbuf[r + 1], w01 = wbuf[r + 2], w11 = wbuf[r + 3];
 #pragma unroll
-                for (int k = 0; k < VPL; ++k) {
-                    if (lane + 32 * k < nvec) {
-                        const V16 val = V16::load_shared(row + (k << 9));
+                    for (int k = 0; k < VPL; ++k) {
+                        if (lane + 32 * k < nvec) {
+                            const V16 f00 = V16::load_shared(row + (k << 9));
+                            const V16 f10 = V16::load_shared(row + p.chunk_bytes + (k << 9));
+                            const V16 f01 = V16::load_shared(row + 2 * p.chunk_bytes + (k << 9));
+                            const V16 f11 = V16::load_shared(row + 3 * p.chunk_bytes + (k << 9));
 #pragma unroll
-                        for (int e = 0; e < E; ++e) acc[k][e] = __fadd_rn(acc[k][e], val.v[e]);
+                            for (int e = 0; e < E; ++e)
+                                acc[k][e] += w00 * f00.v[e] + w10 * f10.v[e] + w01 * f01.v[e] + w11 * f11.v[e];
+                        }
+                    }
+                }
+            } else {
+                for (int r = 0; r < filled; ++r, row += p.chunk_bytes) {
+#pragma unroll
+                    for (int k = 0; k < VPL; ++k) {
+                        if (lane + 32 * k < nvec) {
+                            const V16 val = V16::load_shared(row + (k << 9));
+#pragma unroll
+                            for (int e = 0; e < E; ++e) acc[k][e] = __fadd_rn(acc[k][e], val.v[e]);
+                        }
                     }
                 }
             }
@@ -142,25 +166,60 @@ aggregate_views_kernel(const __grid_constant__ AggParams p) {
         for (int v0 = 0; v0 < p.V; v0 += 32) {
             const int view = v0 + lane;
             int64_t off = -1;
+            int64_t off4[4] = {0, 0, 0, 0};
+            float w4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
             if (view < p.V) {
-                int px, py;
-                if (project_voxel(sP + view, Vpad, wx, wy, wz, p.H, p.W, px, py))
-                    off = (py * p.stride_y + px * p.stride_x) * esz;
+                if (BILINEAR) {
+                    const float *P = sP + view;
+                    const float cx = row_dot4(P[0 * Vpad], P[1 * Vpad], P[2 * Vpad], P[3 * Vpad], wx, wy, wz, 1.0f);
+                    const float cy = row_dot4(P[4 * Vpad], P[5 * Vpad], P[6 * Vpad], P[7 * Vpad], wx, wy, wz, 1.0f);
+                    const float cz = row_dot4(P[8 * Vpad], P[9 * Vpad], P[10 * Vpad], P[11 * Vpad], wx, wy, wz, 1.0f);
+                    const float fx = __fdiv_rn(cx, cz), fy = __fdiv_rn(cy, cz);
+                    if (in_frustum(rintf(fx), rintf(fy), cz, p.H, p.W)) {   // the reference's mask (rm.py:58)
+                        const float x0f = floorf(fx), y0f = floorf(fy);
+                        const float ax = fx - x0f, ay = fy - y0f;
+                        const int x0 = min(max((int)x0f, 0), p.W - 1), x1 = min(max((int)x0f + 1, 0), p.W - 1);
+                        const int y0 = min(max((int)y0f, 0), p.H - 1), y1 = min(max((int)y0f + 1, 0), p.H - 1);
+                        off = 0;
+                        off4[0] = (y0 * p.stride_y + x0 * p.stride_x) * esz;
+                        off4[1] = (y0 * p.stride_y + x1 * p.stride_x) * esz;
+                        off4[2] = (y1 * p.stride_y + x0 * p.stride_x) * esz;
+                        off4[3] = (y1 * p.stride_y + x1 * p.stride_x) * esz;
+                        w4[0] = (1.0f - ax) * (1.0f - ay);
+                        w4[1] = ax * (1.0f - ay);
+                        w4[2] = (1.0f - ax) * ay;
+                        w4[3] = ax * ay;
+                    }
+                } else {
+                    int px, py;
+                    if (project_voxel(sP + view, Vpad, wx, wy, wz, p.H, p.W, px, py))
+                        off = (py * p.stride_y + px * p.stride_x) * esz;
+                }
             }
             const unsigned bits = __ballot_sync(0xffffffffu, off >= 0);
             const int n = __popc(bits);
             const int rank = __popc(bits & ((1u << lane) - 1u));
             cnt += n;
+            constexpr int kSlots = BILINEAR ? 4 : 1;   // buffer slots per visible view
             int done = 0;   // visible views of this round already issued
             while (done < n) {
-                if (filled == p.rows_cap) drain();
-                const int take = min(p.rows_cap - filled, n - done);
-                if (lane == 0) mbar_expect_tx(bar, (uint32_t)(take * p.chunk_bytes));
+                if (filled + kSlots > p.rows_cap) drain();
+                const int take = min((p.rows_cap - filled) / kSlots, n - done);
+                if (lane == 0) mbar_expect_tx(bar, (uint32_t)(take * kSlots * p.chunk_bytes));
                 __syncwarp();
-                if (off >= 0 && rank >= done && rank < done + take)
-                    bulk_g2s(buf0 + (uint32_t)((filled + rank - done) * p.chunk_bytes), sView[view] + off,
-                             (uint32_t)p.chunk_bytes, bar);
-                filled += take;
+                if (off >= 0 && rank >= done && rank < done + take) {
+                    const int slot = filled + (rank - done) * kSlots;
+                    if (BILINEAR) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            bulk_g2s(buf0 + (uint32_t)((slot + q) * p.chunk_bytes), sView[view] + off4[q], (uint32_t)p.chunk_bytes, bar);
+                            wbuf[slot + q] = w4[q];
+                        }
+                    } else {
+                        bulk_g2s(buf0 + (uint32_t)(slot * p.chunk_bytes), sView[view] + off, (uint32_t)p.chunk_bytes, bar);
+                    }
+                }
+                filled += take * kSlots;
                 done += take;
             }
         }
@@ -211,12 +270,12 @@ static int plan_chunk_bytes(int row_bytes, int max_chunk_bytes) {
     return best * 16;
 }
 
-template <int VPL, typename T>
+template <int VPL, typename T, bool BILINEAR = false>
 static cudaError_t launch_agg(const AggParams &p, int chunks, cudaStream_t stream) {
     const int Vpad = p.V | 1;
     const size_t head = (8 * (kAggThreads / kWarp) + sizeof(void *) * p.V + sizeof(float) * 12 * Vpad + 127) & ~(size_t)127;
-    const size_t smem = head + (size_t)(kAggThreads / kWarp) * p.rows_cap * p.chunk_bytes;
-    auto kernel = aggregate_views_kernel<VPL, T>;
+    const size_t smem = head + (size_t)(kAggThreads / kWarp) * p.rows_cap * (p.chunk_bytes + (BILINEAR ? sizeof(float) : 0));
+    auto kernel = aggregate_views_kernel<VPL, T, BILINEAR>;
     // launch configuration cached per (kernel instantiation, device, smem size): the attribute / occupancy queries
     // cost more than the launch itself
     struct Cached { int dev = -1; size_t smem = 0; int ctas = 0; };
@@ -249,13 +308,19 @@ static cudaError_t run_aggregate(const AggParams &p_in, int dtype, int max_chunk
     if (max_chunk_bytes <= 0 || max_chunk_bytes > kMaxChunkBytes) max_chunk_bytes = kMaxChunkBytes;
     p.chunk_bytes = plan_chunk_bytes(p.C * esz, max_chunk_bytes);
     const int chunks = (p.C * esz) / p.chunk_bytes;
-    int warp_buffer = kWarpBufferBytes;
+    int warp_buffer = p.bilinear ? 2 * kWarpBufferBytes : kWarpBufferBytes;   // bilinear: 2 CTAs per SM, 12 KB per warp
     if (const char *env = std::getenv("CNRMA_AGG_WARP_BUFFER")) warp_buffer = std::atoi(env);   // tuning aid
     p.rows_cap = warp_buffer / p.chunk_bytes;
     if (p.rows_cap < 1) p.rows_cap = 1;
     if (p.rows_cap > 32) p.rows_cap = 32;
+    if (p.bilinear) p.rows_cap = p.rows_cap < 4 ? 4 : (p.rows_cap & ~3);
     const int vpl = (p.chunk_bytes / 16 + 31) / 32;
     auto launch = [&](const AggParams &q, int nchunks) -> cudaError_t {
+        if (q.bilinear) {
+            if (dtype == CNRMA_BF16)
+                return vpl == 1 ? launch_agg<1, __nv_bfloat16, true>(q, nchunks, stream) : launch_agg<2, __nv_bfloat16, true>(q, nchunks, stream);
+            return vpl == 1 ? launch_agg<1, float, true>(q, nchunks, stream) : launch_agg<2, float, true>(q, nchunks, stream);
+        }
         if (dtype == CNRMA_BF16)
             return vpl == 1 ? launch_agg<1, __nv_bfloat16>(q, nchunks, stream) : launch_agg<2, __nv_bfloat16>(q, nchunks, stream);
         return vpl == 1 ? launch_agg<1, float>(q, nchunks, stream) : launch_agg<2, float>(q, nchunks, stream);
@@ -284,8 +349,8 @@ cudaError_t run_aggregate_views(const GridDev &g, const cnrma_features &f, int v
     // (cnrma_stage_a_list.cu), whose lane <-> voxel projection needs a third of the instructions.
     const int row_bytes = f.channels * ((f.dtype == CNRMA_BF16) ? 2 : 4);
     // (beyond ~96 views the per-voxel lists no longer fit 32 voxels per warp and the list kernel loses its edge)
-    bool use_list = (row_bytes < 512 && nv <= kListViewsMax) || nv == 0;
-    if (const char *env = std::getenv("CNRMA_AGG_KERNEL")) use_list = (env[0] == 'l');   // tuning aid: "list" / "tma"
+    bool use_list = ((row_bytes < 512 && nv <= kListViewsMax) || nv == 0) && !(flags & kAggBilinearInternal);
+    if (const char *env = std::getenv("CNRMA_AGG_KERNEL")) use_list = (env[0] == 'l') && !(flags & kAggBilinearInternal);   // tuning aid: "list" / "tma"
     if (use_list && list_kernel_supports(nv, f.height, f.width))
         return run_aggregate_list(g, f, v0, nv, proj, proj_stride, stride, flags, volume, vsv, vsc, count, valid, stream);
     AggParams p;
@@ -312,6 +377,8 @@ cudaError_t run_aggregate_views(const GridDev &g, const cnrma_features &f, int v
     for (int i = 0; i < nv; ++i) p.views[i] = f.view_ptrs_host[v0 + i];
     p.chunk_bytes = 0;
     p.rows_cap = 0;
+    p.bilinear = (flags & kAggBilinearInternal) ? 1 : 0;
+    p.flags = flags & ~kAggBilinearInternal;
     p.sweep = make_sweep(g.nx, g.ny, g.nz, sweep_thickness(g.ny, g.nz, nv, row_bytes));
     return run_aggregate(p, f.dtype, max_chunk_bytes, stream);
 }

@@ -444,6 +444,13 @@ def _check_bilinear(cn, sc, dtype):
     vol, cnt, valid = cn.aggregate_views_bilinear(p, f, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
     _v, cnt_nearest, _ = cn.aggregate_views(p, f, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
     assert torch.equal(cnt, cnt_nearest)
+    import os
+    os.environ["CNRMA_BILINEAR_SIMPLE"] = "1"        # the first, straightforward kernel: same formula, same order
+    try:
+        vol_simple, cnt_simple, _ = cn.aggregate_views_bilinear(p, f, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
+    finally:
+        del os.environ["CNRMA_BILINEAR_SIMPLE"]
+    assert torch.equal(cnt, cnt_simple) and torch.equal(vol, vol_simple)
     nx, ny, nz = sc.voxel_dim
     g = torch.stack(torch.meshgrid(torch.arange(nx), torch.arange(ny), torch.arange(nz), indexing="ij"), 0).reshape(3, -1)
     # Positions: torch.mm on the CPU is the same k-ordered FMA chain the kernel uses (see the oracle header), so the
