@@ -11,6 +11,8 @@
 // bulk asynchronous reduction per view (TMA, cp.reduce.async.bulk.global.shared::cta.add.f32) -- fp32 atomics
 // performed by the memory system, like the index_put_(accumulate=True) autograd runs for the reference.
 // Stage B: one CTA per 256 rays like the fill kernel; every ray owns its pixel, so there are no atomics at all.
+#include <cstdlib>
+
 #include "cnrma_internal.cuh"
 
 namespace cnrma {
@@ -98,9 +100,184 @@ __global__ void __launch_bounds__(kAggThreads, 4) aggregate_views_backward_kerne
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// ---- Stage A backward, short rows --------------------------------------------------------------------------
+// Rows below 512 bytes (the reference's 32-channel maps: 128 bytes): one bulk reduction per (voxel, view) is mostly
+// overhead (reference grid: 3.6 ms).  Organised like the forward list kernel (cnrma_stage_a_list.cu): phase 1
+// lane <-> voxel projects a batch of 32 voxels through the views and appends the row offsets of the views that see each
+// voxel to per-voxel lists in shared memory; phase 2 lane group <-> voxel loads the voxel's gradient (16 bytes per
+// lane, divided by the count once) and adds it into every listed pixel row with one vector reduction per lane
+// (red.global.add.v4.f32).  Needs equally spaced gradient maps (one [V,...] tensor) and a power-of-two number of
+// 16-byte vectors per row; everything else takes the bulk-reduction kernel above.
+struct AggBwdListParams {
+    GridDev g;
+    int V, H, W, nvox;
+    float stride;
+    const float *proj;
+    int64_t proj_stride;
+    const float *grad_volume;
+    int64_t vsv, vsc;
+    const int32_t *count;
+    uint32_t flags;
+    int nb, lcap;
+    SweepOrder sweep;
+    unsigned char *view0;                       // gradient maps: view v at view0 + v * view_stride16 * 16
+    uint32_t view_stride16, stride_y16, stride_x16;
+};
+
+__device__ __forceinline__ void red_add_v4(float *dst, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+constexpr int kBwdListThreads = 256;
+
+template <int G>
+__global__ void __launch_bounds__(kBwdListThreads) aggregate_views_backward_list_kernel(const AggBwdListParams p) {
+    constexpr int kWarps = kBwdListThreads / kWarp;
+    constexpr int kVPW = kWarp / G;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *sP = reinterpret_cast<float *>(smem_raw);                                  // [V][12]
+    uint32_t *sList = reinterpret_cast<uint32_t *>(smem_raw + sizeof(float) * 12 * p.V);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *my_lists = sList + (size_t)warp * p.nb * p.lcap;
+    for (int i = threadIdx.x; i < 12 * p.V; i += blockDim.x) {
+        const int v = i / 12, k = i % 12;
+        float val = __ldg(p.proj + (int64_t)v * p.proj_stride + k);
+        if (k < 8) val = __fdiv_rn(val, p.stride);
+        sP[i] = val;
+    }
+    __syncthreads();
+    const int grp = lane / G, lig = lane % G;
+    const int units = (p.nvox + p.nb - 1) / p.nb;
+    const int warps_total = gridDim.x * kWarps;
+    const float fW = (float)p.W - 0.5f, fH = (float)p.H - 0.5f;
+    for (int u = blockIdx.x * kWarps + warp; u < units; u += warps_total) {
+        const int it = u * p.nb + lane;
+        const bool active = lane < p.nb && it < p.nvox;
+        int vx, vy, vz;
+        sweep_voxel(p.sweep, active ? it : 0, vx, vy, vz);
+        const int vox = (vx * p.g.ny + vy) * p.g.nz + vz;
+        const int total = active ? __ldg(p.count + vox) : 0;      // the forward's view count (0: nothing to do)
+        const float wx = world_coord(vx, p.g.vs, p.g.ox);
+        const float wy = world_coord(vy, p.g.vs, p.g.oy);
+        const float wz = world_coord(vz, p.g.vs, p.g.oz);
+        uint32_t *lst = my_lists + lane * p.lcap;
+        int cnt = 0;
+        if (__any_sync(0xffffffffu, total > 0)) {
+            for (int v = 0; v < p.V; ++v) {
+                const float4 a = *reinterpret_cast<const float4 *>(sP + 12 * v);
+                const float4 b = *reinterpret_cast<const float4 *>(sP + 12 * v + 4);
+                const float4 c = *reinterpret_cast<const float4 *>(sP + 12 * v + 8);
+                const float cx = row_dot4(a.x, a.y, a.z, a.w, wx, wy, wz, 1.0f);
+                const float cy = row_dot4(b.x, b.y, b.z, b.w, wx, wy, wz, 1.0f);
+                const float cz = row_dot4(c.x, c.y, c.z, c.w, wx, wy, wz, 1.0f);
+                const float slack = 1.0e-3f * cz;   // conservative pre-test, as in the forward list kernel
+                const bool maybe = (total > 0) && (cz > 0.0f) && (cx + 0.5f * cz >= -slack) && (fW * cz - cx >= -slack) &&
+                                   (cy + 0.5f * cz >= -slack) && (fH * cz - cy >= -slack);
+                if (!__any_sync(0xffffffffu, maybe)) continue;
+                float rx, ry;
+                rounded_pixel(cx, cy, cz, rx, ry);
+                if (total > 0 && in_frustum(rx, ry, cz, p.H, p.W))
+                    lst[cnt++] = (uint32_t)v * p.view_stride16 + (uint32_t)(int)ry * p.stride_y16 + (uint32_t)(int)rx * p.stride_x16;
+            }
+        }
+        __syncwarp();
+        for (int b0 = 0; b0 < p.nb; b0 += kVPW) {
+            const int j = b0 + grp;
+            const int jcnt = __shfl_sync(0xffffffffu, cnt, j & 31);
+            const int jvox = __shfl_sync(0xffffffffu, vox, j & 31);
+            const int jtot = __shfl_sync(0xffffffffu, total, j & 31);
+            if (j >= p.nb || jcnt == 0) continue;
+            const float *src = p.grad_volume + (int64_t)jvox * p.vsv + (int64_t)(lig * 4) * p.vsc;
+            float g0 = __ldg(src), g1 = __ldg(src + p.vsc), g2 = __ldg(src + 2 * p.vsc), g3 = __ldg(src + 3 * p.vsc);
+            if (p.flags & CNRMA_AGG_MEAN) {   // d(sum / count) = d / count
+                const float n = (float)jtot, y = __frcp_rn(n);
+                g0 = div_by_count(g0, n, y);
+                g1 = div_by_count(g1, n, y);
+                g2 = div_by_count(g2, n, y);
+                g3 = div_by_count(g3, n, y);
+            }
+            const uint32_t *jl = my_lists + j * p.lcap;
+            for (int k = 0; k < jcnt; ++k)
+                red_add_v4(reinterpret_cast<float *>(p.view0 + (int64_t)jl[k] * 16 + lig * 16), g0, g1, g2, g3);
+        }
+        __syncwarp();
+    }
+}
+
+// Returns cudaErrorNotSupported when the shape does not fit the list kernel (the caller then uses the bulk kernel).
+static cudaError_t run_aggregate_views_backward_list(const GridDev &g, const cnrma_features &gf, const float *proj,
+                                                     int64_t proj_stride, float stride, uint32_t flags,
+                                                     const float *grad_volume, int64_t vsv, int64_t vsc,
+                                                     const int32_t *count, cudaStream_t stream) {
+    const int nvec = gf.channels / 4;
+    const int nv = gf.views;
+    if (gf.channels % 4 != 0 || nvec > 32 || (nvec & (nvec - 1)) != 0 || nv < 1 || nv > kListViewsMax) return cudaErrorNotSupported;
+    if ((gf.stride_y * 4) % 16 != 0 || (gf.stride_x * 4) % 16 != 0) return cudaErrorNotSupported;
+    const intptr_t base = reinterpret_cast<intptr_t>(gf.view_ptrs_host[0]);
+    const intptr_t step = nv > 1 ? reinterpret_cast<intptr_t>(gf.view_ptrs_host[1]) - base : 0;
+    if (step < 0 || step % 16 != 0) return cudaErrorNotSupported;
+    for (int i = 2; i < nv; ++i)
+        if (reinterpret_cast<intptr_t>(gf.view_ptrs_host[i]) - base != (intptr_t)i * step) return cudaErrorNotSupported;
+    const int64_t span = (int64_t)(nv - 1) * step + (int64_t)gf.height * gf.stride_y * 4 + (int64_t)gf.width * gf.stride_x * 4;
+    if (span / 16 >= ((int64_t)1 << 32)) return cudaErrorNotSupported;
+    AggBwdListParams p;
+    p.g = g;
+    p.V = nv; p.H = gf.height; p.W = gf.width;
+    p.nvox = g.nx * g.ny * g.nz;
+    p.stride = stride;
+    p.proj = proj;
+    p.proj_stride = proj_stride;
+    p.grad_volume = grad_volume;
+    p.vsv = vsv; p.vsc = vsc;
+    p.count = count;
+    p.flags = flags;
+    p.lcap = nv | 1;
+    int nb = 32;
+    while (nb > 1 && (size_t)nb * p.lcap * 4 > 8192) nb >>= 1;
+    if (nb < 32 / nvec) nb = 32 / nvec;
+    p.nb = nb;
+    p.sweep = make_sweep(g.nx, g.ny, g.nz, sweep_thickness(g.ny, g.nz, nv, gf.channels * 4));
+    p.view0 = static_cast<unsigned char *>(const_cast<void *>(gf.view_ptrs_host[0]));
+    p.view_stride16 = (uint32_t)(step / 16);
+    p.stride_y16 = (uint32_t)(gf.stride_y * 4 / 16);
+    p.stride_x16 = (uint32_t)(gf.stride_x * 4 / 16);
+    const size_t smem = sizeof(float) * 12 * nv + sizeof(uint32_t) * (size_t)(kBwdListThreads / kWarp) * p.nb * p.lcap;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int units = (p.nvox + p.nb - 1) / p.nb;
+    const int needed = (units + (kBwdListThreads / kWarp) - 1) / (kBwdListThreads / kWarp);
+    auto go = [&](auto kernel) -> cudaError_t {
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        int per_sm = 0;
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBwdListThreads, smem);
+        if (err != cudaSuccess) return err;
+        const int ctas = sms * (per_sm > 0 ? per_sm : 1);
+        kernel<<<needed < ctas ? needed : ctas, kBwdListThreads, smem, stream>>>(p);
+        return cudaGetLastError();
+    };
+    switch (nvec) {
+        case 1: return go(aggregate_views_backward_list_kernel<1>);
+        case 2: return go(aggregate_views_backward_list_kernel<2>);
+        case 4: return go(aggregate_views_backward_list_kernel<4>);
+        case 8: return go(aggregate_views_backward_list_kernel<8>);
+        case 16: return go(aggregate_views_backward_list_kernel<16>);
+        default: return go(aggregate_views_backward_list_kernel<32>);
+    }
+}
+
 cudaError_t run_aggregate_views_backward(const GridDev &g, const cnrma_features &gf, const float *proj,
                                          int64_t proj_stride, float stride, uint32_t flags, const float *grad_volume,
                                          int64_t vsv, int64_t vsc, const int32_t *count, cudaStream_t stream) {
+    // short rows: list kernel with vector reductions (CNRMA_AGG_BWD_KERNEL=bulk|list overrides)
+    bool use_list = gf.channels * 4 < 512;
+    if (const char *env = std::getenv("CNRMA_AGG_BWD_KERNEL")) use_list = (env[0] == 'l');
+    if (use_list) {
+        const cudaError_t e = run_aggregate_views_backward_list(g, gf, proj, proj_stride, stride, flags, grad_volume, vsv, vsc,
+                                                                count, stream);
+        if (e != cudaErrorNotSupported) return e;
+    }
     AggBwdParams p;
     p.g = g;
     p.C = gf.channels; p.H = gf.height; p.W = gf.width;
