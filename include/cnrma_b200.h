@@ -116,7 +116,8 @@ int cnrma_aggregate_views(const cnrma_grid *grid, const cnrma_features *features
  * (BASELINE.json's north_star names a bilinear gather; the reference samples nearest and parity with it wins, so
  * every other entry point samples nearest).  Same validity mask and view count as cnrma_aggregate_views; value =
  * grid_sample(bilinear, border, align_corners=True) at (cx/cz, cy/cz), summed in view order (/ count with
- * CNRMA_AGG_MEAN).  volume f32 [nvox, C] channels-last contiguous; up to 512 views. */
+ * CNRMA_AGG_MEAN).  volume f32 [nvox, C] channels-last contiguous; up to 512 views.  Runs in the same TMA gather
+ * machinery as cnrma_aggregate_views (four bulk copies per visible view). */
 int cnrma_aggregate_views_bilinear(const cnrma_grid *grid, const cnrma_features *features, const float *projections,
                                    int64_t proj_view_stride, float stride, uint32_t flags, float *volume, int32_t *count,
                                    uint8_t *valid, void *stream);
