@@ -877,7 +877,10 @@ cudaError_t run_march(const GridDev &g, const float *pinv, int V, int H, int W, 
 constexpr int kHalfStageBytes = kStageBytes / 2;
 constexpr int kPackedRowBytesMax = 600;   // rows up to this size take the packed kernel (measured: see DESIGN.md K_B3)
 
-template <typename T, int NJ>
+// SELECT: the hand-off's row selection (rm.py:380-402) fused in: only rows with sel_mask != 0 are produced, at output
+// row sel_prefix[row] (an exclusive prefix sum of the mask, so kept rows stay contiguous and in order), with sel_off
+// added to the coordinates (rm.py:365).
+template <typename T, int NJ, bool SELECT>
 __global__ void __launch_bounds__(kRayThreads) fill_rows_packed_kernel(const __grid_constant__ FillParams p) {
     extern __shared__ __align__(128) unsigned char stage_raw[];
     __shared__ int s_warp_rows[kRayThreads / kWarp];
@@ -901,8 +904,16 @@ __global__ void __launch_bounds__(kRayThreads) fill_rows_packed_kernel(const __g
     for (int i = 0; i < warp; ++i) base += s_warp_rows[i];
     const int64_t my_off = base + (incl - my_cnt);
     // rows beyond the output capacity are dropped (speculative launches): clamp every ray's count once
-    const int my_keep = (int)min((int64_t)my_cnt, max((int64_t)0, p.capacity - my_off));
-    const int64_t warp_off = __shfl_sync(0xffffffffu, my_off, 0);       // the warp's rows are contiguous from here
+    int my_keep = (int)min((int64_t)my_cnt, max((int64_t)0, p.capacity - my_off));
+    int64_t my_out0 = my_off;                                           // output row of my ray's first produced row
+    if (SELECT) {
+        my_keep = 0;
+        for (int k = 0; k < my_cnt; ++k) my_keep += __ldg(p.sel_mask + my_off + k) ? 1 : 0;
+        my_out0 = (my_cnt > 0) ? (int64_t)__ldg(p.sel_prefix + my_off) : 0;
+    }
+    const unsigned with_rows = __ballot_sync(0xffffffffu, my_cnt > 0);
+    const int first_lane = with_rows ? (__ffs(with_rows) - 1) : 0;
+    const int64_t warp_off = __shfl_sync(0xffffffffu, my_out0, first_lane);   // the warp's rows are contiguous from here
     unsigned char *const warp_gbase = reinterpret_cast<unsigned char *>(p.rows) + warp_off * (int64_t)((p.C + (p.normalize ? 3 : 4)) * 4);
     int rows_done = 0;                                                  // rows of this warp already staged
     const float mean = p.normalize ? __ldg(p.mean) : 1.0f;
@@ -969,14 +980,51 @@ __global__ void __launch_bounds__(kRayThreads) fill_rows_packed_kernel(const __g
             const int c = j * 32 + lane;
             f[j] = (c < p.C) ? load_feat<T>(feat + c) : 0.0f;
         }
-        for (int k0 = 0; k0 < cnt; k0 += 32) {
-            const int nk = min(32, cnt - k0);
+        const int cnt_all = SELECT ? __shfl_sync(0xffffffffu, my_cnt, r) : cnt;      // records of the ray (cnt: rows produced)
+        const int64_t row0 = SELECT ? __shfl_sync(0xffffffffu, my_off, r) : 0;          // un-selected index of its first row
+        for (int k0 = 0; k0 < cnt_all; k0 += 32) {
+            const int nk = min(32, cnt_all - k0);
             float wk = 0.0f, wraw = 0.0f, pos[3] = {0.0f, 0.0f, 0.0f};
-            if (lane < nk) {
+            bool sel = lane < nk;
+            if (SELECT && sel) sel = __ldg(p.sel_mask + row0 + k0 + lane) != 0;
+            if (sel) {
                 wraw = __ldg(p.rec_w + (int64_t)(k0 + lane) * p.rays + ray);
                 const float fi = __ldg(p.rec_i + (int64_t)(k0 + lane) * p.rays + ray);
                 record_position(p, o, d, fi, pos);
+                if (SELECT) {   // coord + offsets[b]: one more rounding (rm.py:365)
+                    pos[0] = __fadd_rn(pos[0], p.sel_off[0]);
+                    pos[1] = __fadd_rn(pos[1], p.sel_off[1]);
+                    pos[2] = __fadd_rn(pos[2], p.sel_off[2]);
+                }
                 wk = p.normalize ? __fdiv_rn(wraw, mean) : 1.0f;   // weights / mean(weights), rm.py:303
+            }
+            if (SELECT) {   // row by row over the selected records
+                unsigned bits = __ballot_sync(0xffffffffu, sel);
+                while (bits) {
+                    const int kk = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    if (srows == 0) {
+                        gbase = warp_gbase + (int64_t)rows_done * row_bytes;
+                        h = (int)(reinterpret_cast<uintptr_t>(gbase) & 15);
+                    }
+                    float *row = reinterpret_cast<float *>(stage_base + sbuf * half_bytes) + (h >> 2) + srows * cols;
+                    const float wn = __shfl_sync(0xffffffffu, wk, kk);
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        const int c = j * 32 + lane;
+                        if (c < p.C) row[col0 + c] = p.normalize ? __fmul_rn(f[j], wn) : f[j];
+                    }
+                    if (lane == kk) {
+                        row[0] = pos[0];
+                        row[1] = pos[1];
+                        row[2] = pos[2];
+                        if (!p.normalize) row[3] = wraw;
+                    }
+                    ++srows;
+                    ++rows_done;
+                    if (srows == rows_per_stage) flush();
+                }
+                continue;
             }
             int k = 0;
             while (k < nk) {
@@ -1039,19 +1087,38 @@ static cudaError_t launch_fill(FillParams &p, int dtype, const void *const *view
         const bool tma = !SCATTER && p.sel_mask == nullptr && p.row_stride == cols && p.C <= 32 * kFillRegs &&
                          cols * 4 <= kStageBytes - 16 &&
                          reinterpret_cast<uintptr_t>(p.rows) % 4 == 0;
-        if (tma) {
-            size_t smem = (size_t)(kRayThreads / kWarp) * kStageBytes;
-            static thread_local int attr_dev[16] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};   // dynamic-smem opt-in, once per device
-            int dev = 0;
-            cudaGetDevice(&dev);
-            const int nj = (p.C + 31) / 32;
-            auto go = [&](auto kernel, int slot) {
-                if (attr_dev[slot] != dev) {
-                    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kRayThreads / kWarp) * kStageBytes));
-                    attr_dev[slot] = dev;
-                }
-                kernel<<<blocks, kRayThreads, smem, stream>>>(p);
-            };
+        size_t smem = (size_t)(kRayThreads / kWarp) * kStageBytes;
+        static thread_local int attr_dev[24] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+                                                -1, -1, -1, -1, -1, -1, -1, -1};   // dynamic-smem opt-in, once per device
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const int nj = (p.C + 31) / 32;
+        auto go = [&](auto kernel, int slot) {
+            if (attr_dev[slot] != dev) {
+                cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kRayThreads / kWarp) * kStageBytes));
+                attr_dev[slot] = dev;
+            }
+            kernel<<<blocks, kRayThreads, smem, stream>>>(p);
+        };
+        // hand-off selection fused in: the packed kernel's SELECT form (CNRMA_FILL_SELECT_KERNEL=scalar: the plain kernel)
+        bool select_packed = !SCATTER && p.sel_mask != nullptr && p.row_stride == cols && p.C <= 32 * kFillRegs &&
+                             cols * 4 <= kHalfStageBytes - 16 && reinterpret_cast<uintptr_t>(p.rows) % 4 == 0;
+        if (const char *env = std::getenv("CNRMA_FILL_SELECT_KERNEL")) select_packed = select_packed && env[0] != 's';
+        if (select_packed) {
+            p.stage_half = (cols * 4 <= 2048 - 16) ? 2048 : kHalfStageBytes;
+            smem = (size_t)(kRayThreads / kWarp) * 2 * p.stage_half;
+            if (dtype == CNRMA_BF16) {
+                if (nj <= 1) go(fill_rows_packed_kernel<__nv_bfloat16, 1, true>, 16);
+                else if (nj <= 2) go(fill_rows_packed_kernel<__nv_bfloat16, 2, true>, 17);
+                else if (nj <= 4) go(fill_rows_packed_kernel<__nv_bfloat16, 4, true>, 18);
+                else go(fill_rows_packed_kernel<__nv_bfloat16, 8, true>, 19);
+            } else {
+                if (nj <= 1) go(fill_rows_packed_kernel<float, 1, true>, 20);
+                else if (nj <= 2) go(fill_rows_packed_kernel<float, 2, true>, 21);
+                else if (nj <= 4) go(fill_rows_packed_kernel<float, 4, true>, 22);
+                else go(fill_rows_packed_kernel<float, 8, true>, 23);
+            }
+        } else if (tma) {
             // short rows: per-ray work dominates -> the packed kernel (CNRMA_FILL_KERNEL=tma|packed overrides)
             bool packed = cols * 4 <= kPackedRowBytesMax;
             if (const char *env = std::getenv("CNRMA_FILL_KERNEL")) packed = (env[0] == 'p') && cols * 4 <= kHalfStageBytes - 16;
@@ -1062,15 +1129,15 @@ static cudaError_t launch_fill(FillParams &p, int dtype, const void *const *view
                 if (const char *env = std::getenv("CNRMA_FILL_STAGE_HALF")) p.stage_half = std::atoi(env);
                 smem = (size_t)(kRayThreads / kWarp) * 2 * p.stage_half;
                 if (dtype == CNRMA_BF16) {
-                    if (nj <= 1) go(fill_rows_packed_kernel<__nv_bfloat16, 1>, 8);
-                    else if (nj <= 2) go(fill_rows_packed_kernel<__nv_bfloat16, 2>, 9);
-                    else if (nj <= 4) go(fill_rows_packed_kernel<__nv_bfloat16, 4>, 10);
-                    else go(fill_rows_packed_kernel<__nv_bfloat16, 8>, 11);
+                    if (nj <= 1) go(fill_rows_packed_kernel<__nv_bfloat16, 1, false>, 8);
+                    else if (nj <= 2) go(fill_rows_packed_kernel<__nv_bfloat16, 2, false>, 9);
+                    else if (nj <= 4) go(fill_rows_packed_kernel<__nv_bfloat16, 4, false>, 10);
+                    else go(fill_rows_packed_kernel<__nv_bfloat16, 8, false>, 11);
                 } else {
-                    if (nj <= 1) go(fill_rows_packed_kernel<float, 1>, 12);
-                    else if (nj <= 2) go(fill_rows_packed_kernel<float, 2>, 13);
-                    else if (nj <= 4) go(fill_rows_packed_kernel<float, 4>, 14);
-                    else go(fill_rows_packed_kernel<float, 8>, 15);
+                    if (nj <= 1) go(fill_rows_packed_kernel<float, 1, false>, 12);
+                    else if (nj <= 2) go(fill_rows_packed_kernel<float, 2, false>, 13);
+                    else if (nj <= 4) go(fill_rows_packed_kernel<float, 4, false>, 14);
+                    else go(fill_rows_packed_kernel<float, 8, false>, 15);
                 }
             } else if (dtype == CNRMA_BF16) {
                 if (nj <= 1) go(fill_rows_tma_kernel<__nv_bfloat16, 1>, 0);

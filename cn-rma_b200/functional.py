@@ -674,6 +674,7 @@ def sample_points_device(n, max_points, seed, device):
     with torch.cuda.device(device):
         _lib.check(lib.cnrma_sample_mask(n, int(max_points), int(seed) & 0xFFFFFFFFFFFFFFFF, C.c_void_p(ws.data_ptr()),
                                          nbytes.value, C.c_void_p(mask.data_ptr()), _stream(device)), "cnrma_sample_mask")
+    mask._cnrma_count = min(int(n), int(max_points))     # exact-k draw: see _mask_count
     return mask
 
 
@@ -690,6 +691,13 @@ def _mask_prefix(mask_dev):
                                      C.c_void_p(prefix.data_ptr()), C.c_void_p(kept.data_ptr()), _stream(device)),
                "cnrma_mask_prefix")
     return prefix, kept
+
+
+def _mask_count(mask):
+    """Number of kept rows.  Masks drawn by sample_points_device carry it (exactly min(n, max_points) by
+    construction), which saves a device reduction and a host synchronisation."""
+    known = getattr(mask, "_cnrma_count", None)
+    return int(known) if known is not None else int(mask.sum())
 
 
 def _to_mask_dev(mask, n, device):
@@ -721,7 +729,7 @@ def switch_pointcloud(points, offsets, max_points=None, masks=None, rng=None):
             mask_dev = torch.ones(n, dtype=torch.bool, device=device)
             n_sel = n
         else:
-            n_sel = int(mask.sum())
+            n_sel = _mask_count(mask)
             mask_dev = _to_mask_dev(mask, n, device)
         out = _lib.empty((n_sel, cols), dtype=torch.float32, device=device)
         if n_sel > 0:
@@ -769,7 +777,7 @@ def rma_points_selected(projections, features, tsdf, voxel_dim, voxel_size, orig
             if mask is None:
                 mask_dev, n_sel = torch.ones(n, dtype=torch.bool, device=device), n
             else:
-                n_sel = int(mask.sum())
+                n_sel = _mask_count(mask)
                 mask_dev = _to_mask_dev(mask, n, device)
             cols = fs.C + 3
             out = _lib.empty((n_sel, cols), dtype=torch.float32, device=device)
