@@ -3,7 +3,7 @@
 // rows -- and scenes with many more voxels than pixels, where the TMA kernel's per-voxel projection rounds and
 // per-row issue / drain overhead, not DRAM, set the time (ref test config, 256x256x96 x 50 views x 32 ch: 6.5 ms).
 //
-//   phase 1  lane <-> voxel: a warp takes a batch of up to 32 consecutive voxels of the z-slice sweep and walks the
+//   phase 1  lane <-> voxel: a warp takes a batch of up to 32 consecutive voxels of the sweep order (slabs of z-slices, cnrma_common.cuh) and walks the
 //            views in order; the camera matrix of the current view is warp-uniform (broadcast shared-memory reads),
 //            every lane projects its own voxel and appends the pixel of each view that sees it to its voxel's list in
 //            shared memory.  One projection serves 32 voxels: ~1.2 warp instructions per (voxel, view) instead of ~3.
