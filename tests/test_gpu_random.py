@@ -14,47 +14,7 @@ import oracle
 pytestmark = pytest.mark.gpu
 
 
-def _random_scene(rng):
-    dim = tuple(int(v) for v in rng.integers(3, 28, size=3))
-    vs = float(rng.choice([0.04, 0.08, 0.1, 0.137, 0.25, 0.3333]))
-    origin = (rng.uniform(-1, 1, size=3) * rng.choice([0.0, 1.0])).astype(np.float32)
-    V = int(rng.integers(1, 9))
-    C = int(rng.choice([4, 8, 12, 16, 32, 64]))
-    H, W = int(rng.integers(6, 40)), int(rng.integers(6, 48))
-    stride = int(rng.choice([1, 2, 4]))
-    extent = np.array(dim) * vs
-    projs = np.empty((V, 3, 4), np.float32)
-    for v in range(V):
-        f = rng.uniform(0.5, 1.5) * W * stride
-        k = np.array([[f, 0, rng.uniform(0.3, 0.7) * W * stride], [0, f * rng.uniform(0.9, 1.1), rng.uniform(0.3, 0.7) * H * stride],
-                      [0, 0, 1.0]])
-        cam = origin + extent * rng.uniform(-0.3, 1.3, size=3)              # sometimes outside the grid
-        target = origin + extent * rng.uniform(0.0, 1.0, size=3)
-        fwd = target - cam
-        fwd /= max(np.linalg.norm(fwd), 1e-9)
-        if rng.random() < 0.15:
-            fwd = -fwd                                                      # looking away
-        up = np.array([0.0, 0.0, 1.0]) if abs(fwd[2]) < 0.95 else np.array([0.0, 1.0, 0.0])
-        right = np.cross(fwd, up)
-        right /= np.linalg.norm(right)
-        down = np.cross(fwd, right)
-        pose = np.eye(4)
-        pose[:3, 0], pose[:3, 1], pose[:3, 2], pose[:3, 3] = right, down, fwd, cam
-        projs[v] = (k @ np.linalg.inv(pose)[:3]).astype(np.float32)
-    feats = rng.standard_normal((V, C, H, W), dtype=np.float32)
-    kind = rng.integers(0, 3)
-    if kind == 0:
-        tsdf = rng.uniform(-1, 1, size=dim).astype(np.float32)
-    elif kind == 1:                                                          # piecewise constant with a ramp: big empty regions
-        g = np.indices(dim).astype(np.float32)
-        d = np.minimum.reduce([g[a] - 0.2 * dim[a] for a in range(3)] + [0.8 * dim[a] - g[a] for a in range(3)])
-        tsdf = (np.clip(-d / 2.0, -1, 1) * 0.999).astype(np.float32)
-    else:                                                                    # blocks of constant value
-        coarse = rng.choice([-0.999, 0.999, 0.3], size=[(n + 3) // 4 for n in dim]).astype(np.float32)
-        tsdf = np.kron(coarse, np.ones((4, 4, 4), np.float32))[: dim[0], : dim[1], : dim[2]].copy()
-    N = int(rng.choice([40, 97, 300]))
-    thr = float(rng.choice([0.05, 0.02, 0.3]))
-    return dict(dim=dim, vs=vs, origin=origin, stride=stride, projs=projs, feats=feats, tsdf=tsdf, N=N, thr=thr)
+from conftest import random_scene as _random_scene  # noqa: E402
 
 
 @pytest.mark.parametrize("seed", range(int(os.environ.get("CNRMA_RANDOM_SEEDS", "24"))))
