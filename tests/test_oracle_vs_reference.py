@@ -78,3 +78,44 @@ def test_oracle_equals_reference_on_random_scene(seed):
             assert np.array_equal(ro[:, :3].view(np.uint32), ref_rows[:, :3].view(np.uint32))
             assert np.array_equal(ro[:, 4:].view(np.uint32), ref_rows[:, 4:].view(np.uint32))
             assert_rel(ro[:, 3], ref_rows[:, 3], 1e-5, what="neus weights")
+
+
+@pytest.mark.parametrize("seed", range(min(SEEDS, 16)))
+def test_oracle_depth_mode_equals_reference_on_random_scene(seed):
+    """The alternative weights of rm.py:809-956 (first sign change of the TSDF along the ray, triangular weights)."""
+    ref_shim.load_reference()
+    s = random_scene(np.random.default_rng(7000 + seed))
+    dim, vs, origin, stride, N = s["dim"], s["vs"], s["origin"], s["stride"], s["N"]
+    me = ref_shim.make_self(dim, vs, torch.from_numpy(origin).view(1, 3), stride=stride, ray_marching_type="depth",
+                            neus_threshold=None, depth_points=2)
+    feats = torch.from_numpy(s["feats"]).unsqueeze(1)
+    projs = torch.from_numpy(s["projs"]).unsqueeze(1)
+    tsdf = torch.from_numpy(s["tsdf"])[None, None]
+    checked = 0
+    with torch.no_grad():
+        for k in (0, 1, 3):
+            for v in range(feats.shape[0]):
+                ps = projs[v].clone()
+                ps[:, :2] = ps[:, :2] / stride
+                try:
+                    r = me.ray_projection_depth(ps, feats[v], tsdf, grids=N, select_grids=k)
+                except Exception:       # rm.py:277-283 swallows per-view failures
+                    r = None
+                ro = oracle.ray_projection_depth(oracle.scale_projection(s["projs"][v], stride), s["feats"][v], s["tsdf"], dim,
+                                                 vs, origin, N, k)
+                if r is None or r[0] is None:
+                    assert ro is None or ro.shape[0] <= 1
+                    continue
+                ref_rows = r[0].numpy()
+                assert ro is not None and ro.shape == ref_rows.shape, (k, v)
+                assert np.array_equal(ro.view(np.uint32), ref_rows.view(np.uint32)), (k, v)
+                checked += ref_rows.shape[0]
+    _DEPTH_ROWS_CHECKED.append(checked)
+
+
+_DEPTH_ROWS_CHECKED = []
+
+
+def test_depth_sweep_compared_something():
+    """Runs after the sweep above: the random scenes must have produced depth rows to compare."""
+    assert sum(_DEPTH_ROWS_CHECKED) > 1000
