@@ -119,3 +119,67 @@ _DEPTH_ROWS_CHECKED = []
 def test_depth_sweep_compared_something():
     """Runs after the sweep above: the random scenes must have produced depth rows to compare."""
     assert sum(_DEPTH_ROWS_CHECKED) > 1000
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_oracle_fusion_equals_reference_on_random_frames(seed):
+    """GT TSDF fusion (data_prepare/scannet/tsdf.py:402-451): random grids, origins, frame counts and depth maps with
+    holes, fused frame by frame by the unmodified reference class and by the oracle: all volumes bit-exact."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import make_golden_fusion
+    import cnrma_b200
+    ref = make_golden_fusion.load_reference_fusion()
+    rng = np.random.default_rng(9000 + seed)
+    dim = tuple(int(v) for v in rng.integers(6, 26, size=3))
+    vs = float(rng.choice([0.1, 0.25, 0.3]))
+    origin = tuple(float(x) for x in (rng.uniform(-0.5, 0.5, size=3) * rng.choice([0.0, 1.0])))
+    frames, h, w = int(rng.integers(1, 7)), int(rng.integers(12, 40)), int(rng.integers(16, 48))
+    extent = tuple(d * vs for d in dim)
+    P, k, poses = cnrma_b200.synthetic.ring_cameras(frames, h, w, 1, extent, rng, return_poses=True)
+    depth = cnrma_b200.synthetic.room_depth_maps(k, poses, h, w, extent, rng)
+    depth[rng.random(depth.shape) < 0.1] = 0.0                     # holes: no reading
+    color = rng.uniform(0, 255, size=(frames, 3, h, w)).astype(np.float32)
+    label = rng.integers(0, 40, size=(frames, h, w)).astype(np.int64)
+    fus = ref.TSDFFusion(dim, vs, origin, trunc_ratio=3, device=torch.device("cpu"), color=True, label=True)
+    n = int(np.prod(dim))
+    tsdf, weight = np.ones(n, np.float32), np.zeros(n, np.float32)
+    col, lab = np.zeros((3, n), np.float32), -np.ones(n, np.int64)
+    for i in range(frames):
+        fus.integrate(torch.from_numpy(P[i]), torch.from_numpy(depth[i]), torch.from_numpy(color[i]), torch.from_numpy(label[i]))
+        oracle.tsdf_integrate(dim, vs, np.float32(origin), P[i], depth[i], vs * 3, tsdf, weight, color[i], col, label[i], lab)
+    assert int((fus.weight_vol > 0).sum()) > 0
+    assert np.array_equal(weight.view(np.uint32), fus.weight_vol.numpy().view(np.uint32))
+    assert np.array_equal(tsdf.view(np.uint32), fus.tsdf_vol.numpy().view(np.uint32))
+    assert np.array_equal(col.view(np.uint32), fus.color_vol.numpy().view(np.uint32))
+    assert np.array_equal(lab, fus.label_vol.numpy())
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_oracle_head_equals_reference_on_random_volumes(seed):
+    """TSDF head (models/atlas_head.py:38-52): random channel counts, extents and thresholds; values within 1e-5, the
+    sparsified voxels exact, the surface mask identical outside a 1e-5 band around the threshold."""
+    import importlib
+    ref_shim.load_reference()
+    head_mod = importlib.import_module("projects.mvsdetection.models.atlas_head")
+    rng = np.random.default_rng(11000 + seed)
+    torch.manual_seed(11000 + seed)
+    chans = [int(c) for c in rng.integers(2, 24, size=3)]
+    coarse = tuple(int(v) for v in rng.integers(2, 7, size=3))
+    thr = [float(t) for t in rng.choice([0.7, 0.9, 0.99], size=3)]
+    head = head_mod.AtlasTSDFHead(chans, 3, 0.04, 1.05, thr)
+    xs = [float(rng.uniform(1.0, 4.0)) * torch.randn((1, c) + tuple(d * 2 ** i for d in coarse)) for i, c in enumerate(chans[::-1])]
+    with torch.no_grad():
+        out, _ = head(xs)
+    prev = None
+    for i, key in enumerate(head.keys):
+        ref_t = out["scene_tsdf_" + key][0, 0].numpy()
+        w = head.decoders[i].weight.detach().numpy().reshape(-1)
+        # chain on the reference's previous scale so that differences do not accumulate
+        t, m = oracle.tsdf_head_scale(xs[i][0].numpy(), w, prev, 1.05, thr[i - 1] if i > 0 else None)
+        assert np.max(np.abs(t - ref_t)) <= 1e-5
+        if i > 0:
+            up = np.repeat(np.repeat(np.repeat(prev, 2, 0), 2, 1), 2, 2)
+            assert np.array_equal(m, np.abs(up) < np.float32(thr[i - 1]))
+            assert np.array_equal(t[~m], ref_t[~m])
+        prev = ref_t
