@@ -93,3 +93,31 @@ def random_scene(rng):
     N = int(rng.choice([40, 97, 300]))
     thr = float(rng.choice([0.05, 0.02, 0.3]))
     return dict(dim=dim, vs=vs, origin=origin, stride=stride, projs=projs, feats=feats, tsdf=tsdf, N=N, thr=thr)
+
+
+def random_fusion_case(rng):
+    """Random grid / origin / frames / depth maps with holes for the GT TSDF fusion sweeps."""
+    import cnrma_b200
+    dim = tuple(int(v) for v in rng.integers(6, 26, size=3))
+    vs = float(rng.choice([0.1, 0.25, 0.3]))
+    origin = tuple(float(x) for x in (rng.uniform(-0.5, 0.5, size=3) * rng.choice([0.0, 1.0])))
+    frames, h, w = int(rng.integers(1, 7)), int(rng.integers(12, 40)), int(rng.integers(16, 48))
+    extent = tuple(d * vs for d in dim)
+    P, k, poses = cnrma_b200.synthetic.ring_cameras(frames, h, w, 1, extent, rng, return_poses=True)
+    depth = cnrma_b200.synthetic.room_depth_maps(k, poses, h, w, extent, rng)
+    depth[rng.random(depth.shape) < 0.1] = 0.0                     # holes: no reading
+    color = rng.uniform(0, 255, size=(frames, 3, h, w)).astype(np.float32)
+    label = rng.integers(0, 40, size=(frames, h, w)).astype(np.int64)
+    return dict(dim=dim, vs=vs, origin=origin, P=P, depth=depth, color=color, label=label)
+
+
+def oracle_fusion(case):
+    """The oracle's volumes for a random_fusion_case, frame by frame."""
+    import oracle
+    n = int(np.prod(case["dim"]))
+    tsdf, weight = np.ones(n, np.float32), np.zeros(n, np.float32)
+    col, lab = np.zeros((3, n), np.float32), -np.ones(n, np.int64)
+    for i in range(case["P"].shape[0]):
+        oracle.tsdf_integrate(case["dim"], case["vs"], np.float32(case["origin"]), case["P"][i], case["depth"][i],
+                              case["vs"] * 3, tsdf, weight, case["color"][i], col, case["label"][i], lab)
+    return tsdf, weight, col, lab

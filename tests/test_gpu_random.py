@@ -14,6 +14,7 @@ import oracle
 pytestmark = pytest.mark.gpu
 
 
+from conftest import oracle_fusion, random_fusion_case  # noqa: E402
 from conftest import random_scene as _random_scene  # noqa: E402
 
 
@@ -55,3 +56,52 @@ def test_random_scene(seed):
     assert np.array_equal(rows[:, :3].view(np.uint32), ref[:, :3].view(np.uint32))
     assert np.array_equal(rows[:, 4:].view(np.uint32), ref[:, 4:].view(np.uint32))
     assert np.abs(rows[:, 3] - ref[:, 3]).max() <= 1e-5 * max(ref[:, 3].max(), 1e-3)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_fusion(seed):
+    """GT TSDF fusion kernel against the oracle on random frame sets (half frame by frame, half in one launch)."""
+    import cnrma_b200 as cn
+    case = random_fusion_case(np.random.default_rng(9000 + seed))
+    fus = cn.TSDFFusion(case["dim"], case["vs"], case["origin"], trunc_ratio=3, device="cuda", color=True, label=True)
+    P, D = torch.from_numpy(case["P"]).cuda(), torch.from_numpy(case["depth"]).cuda()
+    Cimg, L = torch.from_numpy(case["color"]).cuda(), torch.from_numpy(case["label"]).cuda()
+    half = P.shape[0] // 2
+    for i in range(half):
+        fus.integrate(P[i], D[i], Cimg[i], L[i])
+    if P.shape[0] > half:
+        fus.integrate_frames(P[half:], D[half:], Cimg[half:], L[half:])
+    tsdf, weight, col, lab = oracle_fusion(case)
+    assert np.array_equal(fus.weight_vol.cpu().numpy().view(np.uint32), weight.view(np.uint32))
+    assert np.array_equal(fus.tsdf_vol.cpu().numpy().view(np.uint32), tsdf.view(np.uint32))
+    assert np.array_equal(fus.color_vol.cpu().numpy().view(np.uint32), col.view(np.uint32))
+    assert np.array_equal(fus.label_vol.cpu().numpy(), lab)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_head(seed):
+    """TSDF head kernels against the oracle on random volume pyramids (NCDHW, channels-last, bf16), 1e-5; masks exact
+    given the same previous scale."""
+    import cnrma_b200 as cn
+    rng = np.random.default_rng(11000 + seed)
+    torch.manual_seed(11000 + seed)
+    chans = [int(c) for c in rng.integers(2, 24, size=3)]
+    coarse = tuple(int(v) for v in rng.integers(2, 7, size=3))
+    thr = [float(t) for t in rng.choice([0.7, 0.9, 0.99], size=3)]
+    prev = None
+    for i, c in enumerate(chans[::-1]):
+        dims = tuple(d * 2 ** i for d in coarse)
+        x = float(rng.uniform(1.0, 4.0)) * torch.randn((1, c) + dims)
+        w = torch.randn(c) / c ** 0.5
+        for layout in ("ncdhw", "channels_last", "bf16"):
+            xd = x.cuda()
+            if layout == "channels_last":
+                xd = xd.contiguous(memory_format=torch.channels_last_3d)
+            if layout == "bf16":
+                xd = xd.to(torch.bfloat16)
+            t, m = cn.tsdf_head_scale(xd, w.cuda(), None if prev is None else torch.from_numpy(prev).cuda()[None, None], 1.05,
+                                      thr[i - 1] if i > 0 else 0.0)
+            ot, om = oracle.tsdf_head_scale(xd.float().cpu().numpy()[0], w.numpy(), prev, 1.05, thr[i - 1] if i > 0 else None)
+            assert np.max(np.abs(t[0, 0].cpu().numpy() - ot)) <= 1e-5, (layout, i)
+            assert np.array_equal(m[0, 0].cpu().numpy(), om), (layout, i)
+        prev = ot

@@ -15,7 +15,7 @@ import torch
 
 import oracle
 import ref_shim
-from conftest import assert_rel, random_scene
+from conftest import assert_rel, oracle_fusion, random_fusion_case, random_scene
 
 pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference tree not mounted")
 SEEDS = int(os.environ.get("CNRMA_REFERENCE_SEEDS", "40"))
@@ -128,26 +128,13 @@ def test_oracle_fusion_equals_reference_on_random_frames(seed):
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
     import make_golden_fusion
-    import cnrma_b200
     ref = make_golden_fusion.load_reference_fusion()
-    rng = np.random.default_rng(9000 + seed)
-    dim = tuple(int(v) for v in rng.integers(6, 26, size=3))
-    vs = float(rng.choice([0.1, 0.25, 0.3]))
-    origin = tuple(float(x) for x in (rng.uniform(-0.5, 0.5, size=3) * rng.choice([0.0, 1.0])))
-    frames, h, w = int(rng.integers(1, 7)), int(rng.integers(12, 40)), int(rng.integers(16, 48))
-    extent = tuple(d * vs for d in dim)
-    P, k, poses = cnrma_b200.synthetic.ring_cameras(frames, h, w, 1, extent, rng, return_poses=True)
-    depth = cnrma_b200.synthetic.room_depth_maps(k, poses, h, w, extent, rng)
-    depth[rng.random(depth.shape) < 0.1] = 0.0                     # holes: no reading
-    color = rng.uniform(0, 255, size=(frames, 3, h, w)).astype(np.float32)
-    label = rng.integers(0, 40, size=(frames, h, w)).astype(np.int64)
-    fus = ref.TSDFFusion(dim, vs, origin, trunc_ratio=3, device=torch.device("cpu"), color=True, label=True)
-    n = int(np.prod(dim))
-    tsdf, weight = np.ones(n, np.float32), np.zeros(n, np.float32)
-    col, lab = np.zeros((3, n), np.float32), -np.ones(n, np.int64)
-    for i in range(frames):
-        fus.integrate(torch.from_numpy(P[i]), torch.from_numpy(depth[i]), torch.from_numpy(color[i]), torch.from_numpy(label[i]))
-        oracle.tsdf_integrate(dim, vs, np.float32(origin), P[i], depth[i], vs * 3, tsdf, weight, color[i], col, label[i], lab)
+    case = random_fusion_case(np.random.default_rng(9000 + seed))
+    fus = ref.TSDFFusion(case["dim"], case["vs"], case["origin"], trunc_ratio=3, device=torch.device("cpu"), color=True, label=True)
+    for i in range(case["P"].shape[0]):
+        fus.integrate(torch.from_numpy(case["P"][i]), torch.from_numpy(case["depth"][i]), torch.from_numpy(case["color"][i]),
+                      torch.from_numpy(case["label"][i]))
+    tsdf, weight, col, lab = oracle_fusion(case)
     assert int((fus.weight_vol > 0).sum()) > 0
     assert np.array_equal(weight.view(np.uint32), fus.weight_vol.numpy().view(np.uint32))
     assert np.array_equal(tsdf.view(np.uint32), fus.tsdf_vol.numpy().view(np.uint32))
