@@ -35,8 +35,13 @@ def _close(got, ref, what):
     assert err <= TOL, f"{what}: {err:.2e}"
 
 
+@pytest.mark.parametrize("kernel", ["default", "bulk", "list"])
 @pytest.mark.parametrize("channels_last", [True, False])
-def test_golden_stage_a_gradient(cn, golden, channels_last):
+def test_golden_stage_a_gradient(cn, golden, channels_last, kernel, monkeypatch):
+    """Both Stage A backward kernels (bulk TMA reductions / list kernel with vector reductions) against the
+    reference's own autograd."""
+    if kernel != "default":
+        monkeypatch.setenv("CNRMA_AGG_BWD_KERNEL", kernel)
     g = golden
     f, p, _ = _inputs(g, channels_last)
     vol, cnt, valid = cn.aggregate_views(p, f, g["voxel_dim"], g["voxel_size"], g["origin"], g["stride"], mean=True)
