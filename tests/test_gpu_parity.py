@@ -100,8 +100,12 @@ def _match_rows(got, ref, thr, c_first, what):
     return False
 
 
+@pytest.mark.parametrize("fill", ["default", "tma", "packed"])
 @pytest.mark.parametrize("channels_last", [True, False])
-def test_golden_neus_rows_and_points(cn, golden, channels_last):
+def test_golden_neus_rows_and_points(cn, golden, channels_last, fill, monkeypatch):
+    """The reference's rows through each of the row-writing kernels (TMA-store per ray / packed across rays)."""
+    if fill != "default":
+        monkeypatch.setenv("CNRMA_FILL_KERNEL", fill)
     g = golden
     f = _feats(g, channels_last)
     tsdf = _dev(g["tsdf"])[None, None]

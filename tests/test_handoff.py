@@ -35,8 +35,12 @@ def test_switch_pointcloud_bit_exact(golden):
 
 
 @pytest.mark.gpu
-def test_fused_selected_fill_equals_two_steps(golden):
-    """march + fill of only the kept rows == full point cloud followed by switch_pointcloud."""
+@pytest.mark.parametrize("kernel", ["packed", "scalar"])
+def test_fused_selected_fill_equals_two_steps(golden, kernel, monkeypatch):
+    """march + fill of only the kept rows == full point cloud followed by switch_pointcloud (both forms of the selecting
+    fill: the packed kernel's SELECT variant and the plain scalar kernel)."""
+    if kernel == "scalar":
+        monkeypatch.setenv("CNRMA_FILL_SELECT_KERNEL", "scalar")
     g = golden
     f = torch.from_numpy(g["features"]).cuda().unsqueeze(1)
     p = torch.from_numpy(g["projections"]).cuda().unsqueeze(1)
