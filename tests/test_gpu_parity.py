@@ -57,8 +57,14 @@ def test_golden_indices_and_masks_bit_exact(cn, golden):
     assert np.array_equal(py[:, 0].cpu().numpy()[valid], g["py"][valid])
 
 
+@pytest.mark.parametrize("kernel,slab", [("default", None), ("tma", None), ("list", None), ("tma", "1"), ("list", "3")])
 @pytest.mark.parametrize("channels_last", [True, False])
-def test_golden_stage_a_bit_exact(cn, golden, channels_last):
+def test_golden_stage_a_bit_exact(cn, golden, channels_last, kernel, slab, monkeypatch):
+    """The reference's sums / counts / means through both Stage A kernels and several sweep orders."""
+    if kernel != "default":
+        monkeypatch.setenv("CNRMA_AGG_KERNEL", kernel)
+    if slab is not None:
+        monkeypatch.setenv("CNRMA_AGG_SLAB", slab)
     g = golden
     f = _feats(g, channels_last)
     vol, cnt, valid = cn.aggregate_views(_projs(g), f, g["voxel_dim"], g["voxel_size"], g["origin"], g["stride"],
@@ -525,3 +531,15 @@ def test_speculative_fill_with_wrong_row_hint(cn, channels):
         F._rows_hint[key] = hint
         again = cn.rma_points(p, f, t, *args, grids=sc.grids, threshold=0.05)[0]
         assert again.shape == first.shape and torch.equal(again, first), hint
+
+
+def test_march_prepass_fused_equals_unfused(cn, scene, monkeypatch):
+    """The fused slab pre-pass of the march (sigmoid table + distance field in two launches) tests the boundary on raw TSDF
+    bits instead of sigmoid values: a more conservative field at worst, identical rows always."""
+    sc = scene
+    p, f, t = _scene_tensors(sc)
+    args = (sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
+    fused = cn.rma_points(p, f, t, *args, grids=sc.grids, threshold=0.05)[0].clone()
+    monkeypatch.setenv("CNRMA_MARCH_UNFUSED_PREPASS", "1")
+    unfused = cn.rma_points(p, f, t, *args, grids=sc.grids, threshold=0.05)[0]
+    assert fused.shape == unfused.shape and torch.equal(fused, unfused)
