@@ -89,6 +89,10 @@ _SIGNATURES = {
     "cnrma_tsdf_head_scale_backward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64,
                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "cnrma_aggregate_views_routed": (C.c_int, [C.POINTER(Grid), C.POINTER(Features), C.c_void_p, C.c_int64, C.c_float, C.c_int,
+                                               C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p]),
+    "cnrma_finalize_routed": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "cnrma_selftest_count_division": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
     "cnrma_to_channels_last": (C.c_int, [C.POINTER(Features), C.c_void_p, C.c_void_p]),
     "cnrma_t_one": (C.c_float, [C.POINTER(Grid), C.c_double, C.c_int]),

@@ -149,6 +149,47 @@ int cnrma_aggregate_views_bilinear(const cnrma_grid *grid, const cnrma_features 
     return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
 }
 
+int cnrma_aggregate_views_routed(const cnrma_grid *grid, const cnrma_features *features, const float *projections,
+                                 int64_t proj_view_stride, float stride, int n_owners, int slab_voxels, int row_floats,
+                                 float *const *owner_rows_host, void *stream) {
+    if (!grid_ok(grid) || !features || !projections || !owner_rows_host || !(stride > 0.0f)) return CNRMA_ERR_ARG;
+    if (n_owners < 1 || n_owners > kMaxOwners || slab_voxels < 1) return CNRMA_ERR_ARG;
+    const int fs = features_ok(features, true);
+    if (fs != CNRMA_OK) return fs;
+    if (features->views < 1 || features->views > kMaxViewsPerLaunch) return CNRMA_ERR_UNSUPPORTED;
+    const int64_t nvox = (int64_t)grid->nx * grid->ny * grid->nz;
+    if ((int64_t)n_owners * slab_voxels < nvox || row_floats < features->channels + 1 || row_floats % 4 != 0)
+        return CNRMA_ERR_ARG;
+    OutputRoute route;
+    route.n_owners = n_owners;
+    route.slab = slab_voxels;
+    route.row_floats = row_floats;
+    route.inv_slab = 1.0f / (float)slab_voxels;
+    for (int o = 0; o < n_owners; ++o) {
+        if (!owner_rows_host[o] || reinterpret_cast<uintptr_t>(owner_rows_host[o]) % 16 != 0) return CNRMA_ERR_LAYOUT;
+        route.owner_base[o] = owner_rows_host[o];
+    }
+    const int d = device_ok();
+    if (d != CNRMA_OK) return d;
+    // volume / count pointers are unused in routed mode (the route carries the destinations)
+    const cudaError_t e = run_aggregate_views(to_dev(*grid), *features, 0, features->views, projections, proj_view_stride,
+                                              stride, 0, route.owner_base[0], row_floats, 1, nullptr, nullptr, 0,
+                                              static_cast<cudaStream_t>(stream), &route);
+    return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
+}
+
+int cnrma_finalize_routed(const float *recv, int n_src, int slab_voxels, int row_floats, int rows, int channels, int mean,
+                          float *volume, int32_t *count, uint8_t *valid, void *stream) {
+    if (!recv || !volume || !count || n_src < 1 || slab_voxels < 1 || rows < 0 || rows > slab_voxels || channels < 4 ||
+        channels % 4 != 0 || row_floats < channels + 1 || row_floats % 4 != 0)
+        return CNRMA_ERR_ARG;
+    const int d = device_ok();
+    if (d != CNRMA_OK) return d;
+    const cudaError_t e = run_finalize_routed(recv, n_src, slab_voxels, row_floats, rows, channels, mean, volume, count, valid,
+                                              static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
+}
+
 int cnrma_selftest_count_division(int max_n, uint64_t *mismatches, void *stream) {
     if (!mismatches || max_n < 1 || max_n > 65535) return CNRMA_ERR_ARG;
     const int d = device_ok();

@@ -237,6 +237,23 @@ __device__ __forceinline__ void sweep_voxel(const SweepOrder &s, int it, int &vx
     fast_divmod(xy, s.ny, s.inv_ny, vx, vy);
 }
 
+// Output routing of the view-sharded Stage A over peer memory (cnrma_aggregate_views_routed): the voxels are split
+// into `n_owners` contiguous ranges of `slab` voxels; voxel v belongs to owner v / slab, and its un-normalised sums
+// (C floats) and view count (one float, at [C]) go to row v % slab of that owner's buffer -- a peer-mapped pointer
+// when the owner is another GPU, so the kernel's stores cross NVLink themselves.  n_owners == 0: not routed.
+constexpr int kMaxOwners = 8;
+struct OutputRoute {
+    int n_owners, slab, row_floats;
+    float inv_slab;
+    float *owner_base[kMaxOwners];   // this source's section of each owner's buffer: [slab][row_floats]
+};
+
+__device__ __forceinline__ float *route_row(const OutputRoute &r, int vox) {
+    int o, lv;
+    fast_divmod(vox, r.slab, r.inv_slab, o, lv);
+    return r.owner_base[o] + (int64_t)lv * r.row_floats;
+}
+
 // IEEE-correct a / n for a small positive integer n, given y = RN(1/n): q = RN(a*y); r = a - n*q (exact, FMA);
 // q' = RN(q + r*y) (Markstein).  Values whose residual could leave the normal range take the generic path.
 __device__ __forceinline__ float div_by_count(float a, float n, float y) {

@@ -20,14 +20,17 @@ cudaError_t run_project_views(const GridDev &g, const float *proj, int64_t proj_
                               int W, int32_t *px, int32_t *py, uint8_t *valid, cudaStream_t stream);
 cudaError_t run_aggregate_views(const GridDev &g, const cnrma_features &f, int v0, int nv, const float *proj,
                                 int64_t proj_stride, float stride, uint32_t flags, float *volume, int64_t vsv,
-                                int64_t vsc, int32_t *count, uint8_t *valid, int max_chunk_bytes, cudaStream_t stream);
+                                int64_t vsc, int32_t *count, uint8_t *valid, int max_chunk_bytes, cudaStream_t stream,
+                                const OutputRoute *route = nullptr);
 bool list_kernel_supports(int V, int H, int W);
 cudaError_t run_aggregate_list(const GridDev &g, const cnrma_features &f, int v0, int nv, const float *proj,
                                int64_t proj_stride, float stride, uint32_t flags, float *volume, int64_t vsv, int64_t vsc,
-                               int32_t *count, uint8_t *valid, cudaStream_t stream);
+                               int32_t *count, uint8_t *valid, cudaStream_t stream, const OutputRoute *route = nullptr);
 cudaError_t run_aggregate_bilinear(const GridDev &g, const cnrma_features &f, const float *proj, int64_t proj_stride,
                                    float stride, uint32_t flags, float *volume, int32_t *count, uint8_t *valid,
                                    cudaStream_t stream);
+cudaError_t run_finalize_routed(const float *recv, int n_src, int slab, int row_floats, int rows, int C, int mean,
+                                float *volume, int32_t *count, uint8_t *valid, cudaStream_t stream);
 cudaError_t run_selftest_count_division(int max_n, unsigned long long *mismatches, cudaStream_t stream);
 cudaError_t run_to_channels_last(const void *const *views_host, int views, int dtype, int C, int H, int W, int64_t sc,
                                  int64_t sy, int64_t sx, void *dst, cudaStream_t stream);

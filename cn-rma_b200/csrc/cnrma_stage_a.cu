@@ -45,6 +45,7 @@ struct AggParams {
     int rows_cap;                 // row slots per warp buffer
     SweepOrder sweep;             // traversal order of the voxels
     int bilinear;                 // opt-in variant: four neighbouring rows per visible view
+    OutputRoute route;            // view-sharded output over peer memory (n_owners == 0: plain output)
     const void *views[kMaxViewsPerLaunch];
 };
 
@@ -240,7 +241,7 @@ aggregate_views_kernel(const __grid_constant__ AggParams p) {
             if (j < nvec) {
                 const int c = c0 + j * E;
                 if (p.vec_store) {
-                    float *dst = p.volume + (int64_t)vox * p.vsv + c;
+                    float *dst = (p.route.n_owners > 0 ? route_row(p.route, vox) : p.volume + (int64_t)vox * p.vsv) + c;
 #pragma unroll
                     for (int e = 0; e < E; e += 4)
                         __stcs(reinterpret_cast<float4 *>(dst + e),
@@ -252,7 +253,8 @@ aggregate_views_kernel(const __grid_constant__ AggParams p) {
             }
         }
         if (lane == 0 && blockIdx.y == 0 && p.write_count) {
-            if (p.flags & CNRMA_AGG_COUNT_F32) reinterpret_cast<float *>(p.count)[vox] = (float)cnt;
+            if (p.route.n_owners > 0) route_row(p.route, vox)[p.C] = (float)cnt;
+            else if (p.flags & CNRMA_AGG_COUNT_F32) reinterpret_cast<float *>(p.count)[vox] = (float)cnt;
             else p.count[vox] = cnt;
             if (p.valid != nullptr) p.valid[vox] = (uint8_t)(cnt > 0);
         }
@@ -343,7 +345,8 @@ static cudaError_t run_aggregate(const AggParams &p_in, int dtype, int max_chunk
 // Views [v0, v0 + nv) of `f` in one launch (nv <= kMaxViewsPerLaunch).
 cudaError_t run_aggregate_views(const GridDev &g, const cnrma_features &f, int v0, int nv, const float *proj,
                                 int64_t proj_stride, float stride, uint32_t flags, float *volume, int64_t vsv,
-                                int64_t vsc, int32_t *count, uint8_t *valid, int max_chunk_bytes, cudaStream_t stream) {
+                                int64_t vsc, int32_t *count, uint8_t *valid, int max_chunk_bytes, cudaStream_t stream,
+                                const OutputRoute *route) {
     // Kernel choice (DESIGN.md "K_A"): rows of 512 bytes and more go through the TMA kernel below (DRAM-bound, deep
     // register-free gather queue); shorter rows -- and the finalise-only pass -- through the list kernel
     // (cnrma_stage_a_list.cu), whose lane <-> voxel projection needs a third of the instructions.
@@ -352,7 +355,7 @@ cudaError_t run_aggregate_views(const GridDev &g, const cnrma_features &f, int v
     bool use_list = ((row_bytes < 512 && nv <= kListViewsMax) || nv == 0) && !(flags & kAggBilinearInternal);
     if (const char *env = std::getenv("CNRMA_AGG_KERNEL")) use_list = (env[0] == 'l') && !(flags & kAggBilinearInternal);   // tuning aid: "list" / "tma"
     if (use_list && list_kernel_supports(nv, f.height, f.width))
-        return run_aggregate_list(g, f, v0, nv, proj, proj_stride, stride, flags, volume, vsv, vsc, count, valid, stream);
+        return run_aggregate_list(g, f, v0, nv, proj, proj_stride, stride, flags, volume, vsv, vsc, count, valid, stream, route);
     AggParams p;
     p.g = g;
     p.V = nv;
@@ -372,6 +375,11 @@ cudaError_t run_aggregate_views(const GridDev &g, const cnrma_features &f, int v
     p.valid = valid;
     p.flags = flags;
     p.vec_store = (vsc == 1) && (vsv % 4 == 0) && (reinterpret_cast<uintptr_t>(volume) % 16 == 0);
+    p.route.n_owners = 0;
+    if (route != nullptr) {
+        p.route = *route;
+        p.vec_store = 1;   // routed rows are 16-byte aligned by construction (cnrma_aggregate_views_routed)
+    }
     p.chunk_base = 0;
     p.write_count = 1;
     for (int i = 0; i < nv; ++i) p.views[i] = f.view_ptrs_host[v0 + i];
@@ -453,6 +461,48 @@ cudaError_t run_project_views(const GridDev &g, const float *proj, int64_t proj_
 }
 
 // ---- NCHW -> channels-last ------------------------------------------------------------------------
+// Owner-side pass of the view-sharded Stage A: adds the partial sums and counts that the `n_src` sources stored for
+// this owner's voxels (source order, so the result does not depend on timing) and divides by the total count.
+// recv [n_src][slab][row_floats] (sums at [0, C), count at [C]); volume [rows, C]; count int32 [rows]; valid uint8.
+__global__ void __launch_bounds__(256) finalize_routed_kernel(const float *__restrict__ recv, int n_src, int slab,
+                                                              int row_floats, int rows, int C, int mean,
+                                                              float *__restrict__ volume, int32_t *__restrict__ count,
+                                                              uint8_t *__restrict__ valid) {
+    const int nvec = C / 4;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)rows * nvec) return;
+    const int row = (int)(i / nvec), j = (int)(i % nvec);
+    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float n = 0.0f;
+    for (int s = 0; s < n_src; ++s) {
+        const float *r = recv + ((int64_t)s * slab + row) * row_floats;
+        const float4 v = __ldcs(reinterpret_cast<const float4 *>(r + 4 * j));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        n += __ldg(r + C);
+    }
+    if (mean) {
+        const bool seen = n > 0.0f;
+        acc.x = seen ? __fdiv_rn(acc.x, n) : 0.0f;
+        acc.y = seen ? __fdiv_rn(acc.y, n) : 0.0f;
+        acc.z = seen ? __fdiv_rn(acc.z, n) : 0.0f;
+        acc.w = seen ? __fdiv_rn(acc.w, n) : 0.0f;
+    }
+    __stcs(reinterpret_cast<float4 *>(volume + (int64_t)row * C + 4 * j), acc);
+    if (j == 0) {
+        count[row] = (int32_t)n;
+        if (valid != nullptr) valid[row] = (uint8_t)(n > 0.0f);
+    }
+}
+
+cudaError_t run_finalize_routed(const float *recv, int n_src, int slab, int row_floats, int rows, int C, int mean,
+                                float *volume, int32_t *count, uint8_t *valid, cudaStream_t stream) {
+    const int64_t threads = (int64_t)rows * (C / 4);
+    if (threads == 0) return cudaSuccess;
+    finalize_routed_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(recv, n_src, slab, row_floats, rows, C, mean,
+                                                                             volume, count, valid);
+    return cudaGetLastError();
+}
+
 // Reference-layout (NCHW) maps -> channels-last rows, all views of a stack in one launch: tiles of 32 channels x 64
 // pixels through shared memory, reads coalesced along the pixel axis of the source planes (eight loads in flight per
 // thread), writes coalesced along the channel axis of the destination rows.  Contiguous planes (the usual case) are

@@ -33,6 +33,7 @@ struct ListParams {
     int nb;     // voxels per warp batch (<= 32)
     int lcap;   // list capacity per voxel (odd, >= V)
     SweepOrder sweep;   // traversal order of the voxels (cnrma_common.cuh)
+    OutputRoute route;  // view-sharded output over peer memory (n_owners == 0: plain output)
     // uniform: the views are equally spaced in one allocation, so a list entry is the row's offset from views[0] in
     // 16-byte units (one multiply-add to decode); otherwise entries pack (view, py, px) and go through the pointer table
     int uniform;
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(kListThreads) aggregate_views_list_kernel(cons
             for (int q = 0; q < VPL; ++q) {
                 const int c = c0 + q * G * E;
                 if (p.vec_store) {
-                    float *dst = p.volume + (int64_t)jvox * p.vsv + c;
+                    float *dst = (p.route.n_owners > 0 ? route_row(p.route, jvox) : p.volume + (int64_t)jvox * p.vsv) + c;
 #pragma unroll
                     for (int e = 0; e < E; e += 4)
                         __stcs(reinterpret_cast<float4 *>(dst + e), make_float4(acc[q][e], acc[q][e + 1], acc[q][e + 2], acc[q][e + 3]));
@@ -186,7 +187,8 @@ __global__ void __launch_bounds__(kListThreads) aggregate_views_list_kernel(cons
                 }
             }
             if (lig == 0 && blockIdx.y == 0 && p.write_count) {
-                if (p.flags & CNRMA_AGG_COUNT_F32) reinterpret_cast<float *>(p.count)[jvox] = (float)total;
+                if (p.route.n_owners > 0) route_row(p.route, jvox)[p.C] = (float)total;
+                else if (p.flags & CNRMA_AGG_COUNT_F32) reinterpret_cast<float *>(p.count)[jvox] = (float)total;
                 else p.count[jvox] = total;
                 if (p.valid != nullptr) p.valid[jvox] = (uint8_t)(total > 0);
             }
@@ -243,7 +245,7 @@ bool list_kernel_supports(int V, int H, int W) { return V <= 4096 && H <= 1024 &
 
 cudaError_t run_aggregate_list(const GridDev &g, const cnrma_features &f, int v0, int nv, const float *proj,
                                int64_t proj_stride, float stride, uint32_t flags, float *volume, int64_t vsv, int64_t vsc,
-                               int32_t *count, uint8_t *valid, cudaStream_t stream) {
+                               int32_t *count, uint8_t *valid, cudaStream_t stream, const OutputRoute *route) {
     const int esz = (f.dtype == CNRMA_BF16) ? 2 : 4;
     const int nvec = f.channels * esz / 16;
     // lanes per voxel: the largest power of two <= 32 dividing nvec; the rest as vectors per lane (<= 4) and chunks
@@ -269,6 +271,11 @@ cudaError_t run_aggregate_list(const GridDev &g, const cnrma_features &f, int v0
     p.valid = valid;
     p.flags = flags;
     p.vec_store = (vsc == 1) && (vsv % 4 == 0) && (reinterpret_cast<uintptr_t>(volume) % 16 == 0);
+    p.route.n_owners = 0;
+    if (route != nullptr) {
+        p.route = *route;
+        p.vec_store = 1;
+    }
     p.sweep = make_sweep(g.nx, g.ny, g.nz, sweep_thickness(g.ny, g.nz, nv, f.channels * esz));
     p.lcap = nv | 1;                                      // odd: the lanes' list writes hit different banks
     int nb = 32;                                          // voxels per warp batch: lists must fit ~8 KB per warp

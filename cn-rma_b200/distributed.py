@@ -114,3 +114,84 @@ def rma_points_sharded(projections, features, tsdf, voxel_dim, voxel_size, origi
 
     return F.rma_points(projections, features, tsdf, voxel_dim, voxel_size, origin, stride, grids=grids, mode=mode,
                         threshold=threshold, depth_points=depth_points, normalize=True, mean_hook=global_mean)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# View-sharded Stage A over peer memory: the exchange is done by the gather kernel's own stores
+# ---------------------------------------------------------------------------------------------------------------
+
+def _routed_slab(nvox, owners):
+    return -(-nvox // owners)
+
+
+def route_views(projections, features, voxel_dim, voxel_size, origin, stride, owner_rows):
+    """This rank's views -> un-normalised sums and counts, stored by the kernel into `owner_rows[o]`, this source's
+    [slab, C + 4] section of owner o's buffer (a peer-mapped tensor when o is another GPU).  Batch 1."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    fs = F._FeatureStack(F._as_view_list(features), need_vector_layout=True)
+    if fs.B != 1:
+        raise ValueError("route_views handles one scene at a time")
+    P = F._projections_device(projections, fs.device)
+    nx, ny, nz = (int(v) for v in voxel_dim)
+    slab, row_floats = owner_rows[0].shape[0], owner_rows[0].shape[1]
+    grid = _lib.make_grid(voxel_dim, voxel_size, F._origin3(origin))
+    ptrs = (C.c_void_p * len(owner_rows))(*[t.data_ptr() for t in owner_rows])
+    desc = fs.descriptor(0)
+    with torch.cuda.device(fs.device):
+        _lib.check(lib.cnrma_aggregate_views_routed(C.byref(grid), C.byref(desc), C.c_void_p(P[0, 0].data_ptr()), 12,
+                                                    float(stride), len(owner_rows), slab, row_floats, ptrs,
+                                                    F._stream(fs.device)), "cnrma_aggregate_views_routed")
+
+
+def finalize_routed(recv, rows, channels, mean=True):
+    """recv [n_src, slab, C + 4] (this owner's buffer, every source's section filled) -> (volume [rows, C] f32,
+    count [rows] int32, valid [rows] bool): sums and counts added in source order, then the mean of rm.py:251."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    n_src, slab, row_floats = recv.shape
+    volume = _lib.empty((rows, channels), dtype=torch.float32, device=recv.device)
+    count = _lib.empty((rows,), dtype=torch.int32, device=recv.device)
+    valid = _lib.empty((rows,), dtype=torch.bool, device=recv.device)
+    with torch.cuda.device(recv.device):
+        _lib.check(lib.cnrma_finalize_routed(C.c_void_p(recv.data_ptr()), n_src, slab, row_floats, rows, channels,
+                                             1 if mean else 0, C.c_void_p(volume.data_ptr()), C.c_void_p(count.data_ptr()),
+                                             C.c_void_p(valid.data_ptr()), F._stream(recv.device)), "cnrma_finalize_routed")
+    return volume, count, valid
+
+
+_p2p_buffers = {}
+
+
+def aggregate_views_p2p(projections, features, voxel_dim, voxel_size, origin, stride, group=None):
+    """View-sharded Stage A with the exchange fused into the gather kernel (NVLink peer stores into symmetric memory,
+    torch.distributed._symmetric_memory) instead of an all-reduce of full-size partial volumes.
+
+    `projections` / `features` hold THIS RANK's views (view_shard).  The voxels are split into world_size contiguous
+    ranges; every rank's kernel stores the partial sums of ALL voxels straight into their owners' buffers, a device
+    barrier follows, and each owner adds what it received in rank order and divides.  Returns this rank's slab:
+    (lo, hi, volume [hi - lo, C], count [hi - lo] int32, valid [hi - lo] bool), voxels in the flat order
+    (x * ny + y) * nz + z.  All-gather the slabs if one rank needs the whole volume."""
+    import torch.distributed._symmetric_memory as symm_mem
+    rank, world = _world(group)
+    f0 = features[0]
+    channels, device = f0.shape[1], f0.device
+    nx, ny, nz = (int(v) for v in voxel_dim)
+    nvox = nx * ny * nz
+    slab, row_floats = _routed_slab(nvox, world), channels + 4
+    key = (world, slab, row_floats, device)
+    if key not in _p2p_buffers:
+        buf = symm_mem.empty((world, slab, row_floats), dtype=torch.float32, device=device)
+        hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+        peers = [hdl.get_buffer(o, (world, slab, row_floats), torch.float32) for o in range(world)]
+        _p2p_buffers[key] = (buf, hdl, peers)
+    buf, hdl, peers = _p2p_buffers[key]
+    hdl.barrier(channel=0)                                    # every owner is done reading the previous call's data
+    route_views(projections, features, voxel_dim, voxel_size, origin, stride, [peers[o][rank] for o in range(world)])
+    hdl.barrier(channel=1)                                    # all sources' stores have landed
+    lo = min(rank * slab, nvox)
+    hi = min(lo + slab, nvox)
+    volume, count, valid = finalize_routed(buf, hi - lo, channels)
+    return lo, hi, volume, count, valid

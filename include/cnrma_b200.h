@@ -122,6 +122,22 @@ int cnrma_aggregate_views_bilinear(const cnrma_grid *grid, const cnrma_features 
                                    int64_t proj_view_stride, float stride, uint32_t flags, float *volume, int32_t *count,
                                    uint8_t *valid, void *stream);
 
+/* View-sharded Stage A over peer memory ("by view subset"): instead of an all-reduce of full-size partial
+ * volumes, the voxels are split into n_owners contiguous ranges of slab_voxels voxels, and the kernel stores voxel v's
+ * un-normalised sums (C floats) and view count (one float at [C]) into row v % slab_voxels of owner v / slab_voxels:
+ *   owner_rows_host[o]  HOST array of DEVICE pointers: THIS source's section [slab_voxels][row_floats] of owner o's
+ *                       buffer -- a peer-mapped pointer when o is another GPU (the stores then cross NVLink by
+ *                       themselves, overlapped with the gather); row_floats >= C + 1, multiple of 4, 16-byte aligned rows
+ * After all sources are done (a device barrier between the ranks, the caller's business), every owner runs
+ * cnrma_finalize_routed over its buffer recv [n_src][slab_voxels][row_floats]: partial sums and counts are added in
+ * source order and divided (mean != 0) like rm.py:251; volume f32 [rows, C], count int32 [rows], valid uint8 or NULL.
+ * Indices, masks and counts are exact; the sums are regrouped by source, hence 1e-5. */
+int cnrma_aggregate_views_routed(const cnrma_grid *grid, const cnrma_features *features, const float *projections,
+                                 int64_t proj_view_stride, float stride, int n_owners, int slab_voxels, int row_floats,
+                                 float *const *owner_rows_host, void *stream);
+int cnrma_finalize_routed(const float *recv, int n_src, int slab_voxels, int row_floats, int rows, int channels, int mean,
+                          float *volume, int32_t *count, uint8_t *valid, void *stream);
+
 /* Proof obligation of the fused mean (rm.py:251 `volume / valid`): the kernel divides by the view count with
  * one correctly rounded reciprocal and a Markstein correction instead of a generic division.  This entry
  * point checks that shortcut against IEEE division for every count in [1, max_n] and every fp32 significand

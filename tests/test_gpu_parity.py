@@ -543,3 +543,35 @@ def test_march_prepass_fused_equals_unfused(cn, scene, monkeypatch):
     monkeypatch.setenv("CNRMA_MARCH_UNFUSED_PREPASS", "1")
     unfused = cn.rma_points(p, f, t, *args, grids=sc.grids, threshold=0.05)[0]
     assert fused.shape == unfused.shape and torch.equal(fused, unfused)
+
+
+@pytest.mark.parametrize("channels,owners", [(8, 2), (16, 3), (128, 2), (256, 4)])
+def test_routed_stage_a_single_gpu_simulation(cn, channels, owners):
+    """The view-sharded Stage A over peer memory (cnrma_aggregate_views_routed + cnrma_finalize_routed), with the
+    'peers' simulated by local buffers: each source rank's views are routed into its section of every owner's buffer,
+    the owners finalise, and the slabs put together must equal the single-GPU result (counts exact, means 1e-5:
+    the sums are regrouped by source).  Both Stage A kernels (short and long rows)."""
+    from cnrma_b200 import distributed as D
+    sc = cn.synthetic.make_scene("small", seed=6, channels=channels, views=7)
+    p, f, _ = _scene_tensors(sc)
+    args = (sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
+    want_vol, want_cnt, want_valid = cn.aggregate_views(p, f, *args)
+    nvox = int(np.prod(sc.voxel_dim))
+    slab = D._routed_slab(nvox, owners)
+    bufs = [torch.full((owners, slab, channels + 4), float("nan"), device="cuda") for _ in range(owners)]
+    for src in range(owners):
+        lo, hi = D.view_shard(sc.views, src, owners)
+        D.route_views(p[lo:hi], f[lo:hi], *args, [bufs[o][src] for o in range(owners)])
+    vols, cnts, valids = [], [], []
+    for o in range(owners):
+        rows = min(slab, max(0, nvox - o * slab))
+        v, c, m = D.finalize_routed(bufs[o], rows, channels)
+        vols.append(v)
+        cnts.append(c)
+        valids.append(m)
+    vol = torch.cat(vols).view(*sc.voxel_dim, channels).permute(3, 0, 1, 2)
+    cnt = torch.cat(cnts).view(sc.voxel_dim)
+    assert torch.equal(cnt, want_cnt[0, 0]) and torch.equal(torch.cat(valids).view(sc.voxel_dim), want_valid[0, 0])
+    assert not bool(torch.isnan(vol).any())
+    scale = float(want_vol.abs().max())
+    assert float((vol - want_vol[0]).abs().max()) <= 1e-5 * scale
