@@ -37,7 +37,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-views", type=int, default=0, help="views in the CPU sample (0 = auto)")
     ap.add_argument("--stage", default="both", choices=["both", "a", "b"], help="profiling aid: run one stage only")
-    ap.add_argument("--mode", default="scene-dp", choices=["scene-dp", "view-sharded"],
+    ap.add_argument("--mode", default="scene-dp", choices=["scene-dp", "view-sharded", "view-p2p"],
                     help="N>1: independent scenes per GPU (default) or ONE scene with its views sharded + one all-reduce")
     return ap.parse_args()
 
@@ -252,7 +252,7 @@ def main():
     cn.load()
 
     hbm_peak, peak_src = load_peaks()
-    if args.mode == "view-sharded":
+    if args.mode in ("view-sharded", "view-p2p"):
         run_view_sharded(args, cn, dev, rank, world)
         return
     sc = cn.synthetic.make_scene(args.config, seed=rank, with_features=False)
@@ -433,7 +433,11 @@ def run_view_sharded(args, cn, dev, rank, world):
     feats = full[lo:hi]
     proj = torch.from_numpy(sc.projections).to(dev).unsqueeze(1)[lo:hi]
     del full
-    call = lambda: D.aggregate_views_sharded(proj, feats, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
+    p2p = args.mode == "view-p2p"      # exchange fused into the gather kernel (peer stores) instead of an all-reduce
+    if p2p:
+        call = lambda: D.aggregate_views_p2p(proj, feats, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
+    else:
+        call = lambda: D.aggregate_views_sharded(proj, feats, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
     for _ in range(max(args.warmup, 3)):
         call()
     torch.cuda.synchronize()
@@ -458,7 +462,9 @@ def run_view_sharded(args, cn, dev, rank, world):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.config, sc) + " -- Stage A only, views sharded",
-                       "parallelism": f"view-shard{world} + 1 all-reduce of {nbytes / 1e6:.0f} MB"},
+                       "parallelism": (f"view-shard{world} + peer stores of {nbytes * (world - 1) / world / 1e6:.0f} MB per rank "
+                                       "(output stays sharded by voxel range)") if p2p else
+                                      f"view-shard{world} + 1 all-reduce of {nbytes / 1e6:.0f} MB"},
             "scenes_per_s": 1e3 / ms, "gpu_launches": 2 * args.steps}))
     if world > 1:
         dist.destroy_process_group()

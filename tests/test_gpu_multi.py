@@ -62,3 +62,44 @@ def test_view_sharded_over_nccl():
     assert got["wtot_err"] <= 1e-5 and got["wsum_err"] <= 1e-5
     assert got["rows_total"]
     assert got["pts_err"] <= 1e-5
+
+
+def _worker_p2p(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import cnrma_b200 as cn
+    from cnrma_b200 import distributed as D
+    ok = True
+    for channels in (16, 256):                       # list kernel / TMA kernel
+        sc = cn.synthetic.make_scene("small", seed=22, channels=channels, views=7)
+        lo, hi = D.view_shard(sc.views, rank, world)
+        f = torch.from_numpy(sc.features).to(dev).unsqueeze(1).permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+        p = torch.from_numpy(sc.projections).to(dev).unsqueeze(1)
+        args = (sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
+        v1, c1, m1 = cn.aggregate_views(p, f, *args)                      # all views on this GPU
+        v1 = v1[0].permute(1, 2, 3, 0).reshape(-1, channels)
+        for _ in range(3):                                                # repeated calls reuse the symmetric buffer
+            a, b, vol, cnt, valid = D.aggregate_views_p2p(p[lo:hi], f[lo:hi], *args)
+        ok = ok and bool(torch.equal(cnt, c1.view(-1)[a:b])) and bool(torch.equal(valid, m1.view(-1)[a:b]))
+        err = float((vol - v1[a:b]).abs().max() / v1.abs().max())
+        ok = ok and err <= 1e-5 and (b - a) > 0
+    ret[f"ok{rank}"] = ok
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_view_sharded_over_peer_memory():
+    """aggregate_views_p2p: the kernel's own NVLink stores into symmetric memory instead of an all-reduce."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    port = 29700 + (os.getpid() % 1000)
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker_p2p, args=(2, port, ret), nprocs=2, join=True)
+        got = dict(ret)
+    assert got.get("ok0") and got.get("ok1")
