@@ -58,10 +58,32 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    """Compiles csrc/*.cu for sm_100a into cn-rma_b200/libcnrma_b200.so (in-tree, travels with gpurun)."""
+    """Compiles csrc/*.cu for sm_100a into cn-rma_b200/libcnrma_b200.so (in-tree, travels with gpurun).  The
+    translation units are compiled in parallel (one nvcc per file, objects under csrc/_build/) and linked with
+    nvcc -shared; an object is rebuilt when its source or any header is newer."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(_CSRC, s) for s in SOURCES]
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(_CSRC, "_build")
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = _nvcc()
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    header_time = max(os.path.getmtime(os.path.join(_CSRC, h)) for h in HEADERS)
+
+    def compile_one(src):
+        path = os.path.join(_CSRC, src)
+        obj = os.path.join(objdir, src[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(path), header_time):
+            return obj
+        cmd = [nvcc] + compile_flags + ["-c", path, "-o", obj]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)
