@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libcnrma_b200.so")
 SOURCES = ["cnrma_abi.cu", "cnrma_stage_a.cu", "cnrma_stage_a_list.cu", "cnrma_stage_a_bilinear.cu", "cnrma_tsdf_head.cu", "cnrma_stage_b.cu", "cnrma_backward.cu",
-           "cnrma_handoff.cu", "cnrma_fusion.cu"]
+           "cnrma_handoff.cu", "cnrma_fusion.cu", "cnrma_exchange.cu"]
 HEADERS = ["cnrma_common.cuh", "cnrma_internal.cuh", os.path.join("..", "..", "include", "cnrma_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -30,6 +30,10 @@ class CnrmaError(RuntimeError):
 class Grid(C.Structure):
     _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("voxel_size", C.c_float),
                 ("origin", C.c_float * 3)]
+
+
+class Box(C.Structure):
+    _fields_ = [("lo", C.c_int32 * 3), ("dim", C.c_int32 * 3)]
 
 
 class Features(C.Structure):
@@ -103,6 +107,14 @@ _SIGNATURES = {
     "cnrma_aggregate_views": (C.c_int, [C.POINTER(Grid), C.POINTER(Features), C.c_void_p, C.c_int64, C.c_float,
                                         C.c_uint32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_void_p]),
+    "cnrma_aggregate_views_box": (C.c_int, [C.POINTER(Grid), C.POINTER(Box), C.POINTER(Features), C.c_void_p, C.c_int64,
+                                            C.c_float, C.c_uint32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                            C.c_int, C.c_void_p]),
+    "cnrma_mark_rows": (C.c_int, [C.POINTER(Grid), C.POINTER(Box), C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_void_p]),
+    "cnrma_pull_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                  C.c_int, C.c_void_p]),
+    "cnrma_pull_default_ctas": (C.c_int, []),
     "cnrma_aggregate_views_bilinear": (C.c_int, [C.POINTER(Grid), C.POINTER(Features), C.c_void_p, C.c_int64, C.c_float,
                                                  C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cnrma_tsdf_head_scale": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64,
@@ -188,6 +200,13 @@ def make_grid(voxel_dim, voxel_size, origin):
     g.voxel_size = float(voxel_size)
     g.origin[0], g.origin[1], g.origin[2] = (float(v) for v in origin)
     return g
+
+
+def make_box(lo, dim):
+    b = Box()
+    for a in range(3):
+        b.lo[a], b.dim[a] = int(lo[a]), int(dim[a])
+    return b
 
 
 def empty(*size, **kw):

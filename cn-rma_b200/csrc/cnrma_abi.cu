@@ -85,11 +85,20 @@ int cnrma_project_views(const cnrma_grid *grid, const float *projections, int64_
     return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
 }
 
-int cnrma_aggregate_views(const cnrma_grid *grid, const cnrma_features *features, const float *projections,
-                          int64_t proj_view_stride, float stride, uint32_t flags, float *volume,
-                          int64_t vol_stride_voxel, int64_t vol_stride_channel, int32_t *count, uint8_t *valid,
-                          void *stream) {
+static bool box_ok(const cnrma_grid *g, const cnrma_box *b) {
+    if (!b) return false;
+    const int n[3] = {g->nx, g->ny, g->nz};
+    for (int a = 0; a < 3; ++a)
+        if (b->lo[a] < 0 || b->dim[a] <= 0 || (int64_t)b->lo[a] + b->dim[a] > n[a]) return false;
+    return true;
+}
+
+static int aggregate_views_impl(const cnrma_grid *grid, const cnrma_box *box, const cnrma_features *features,
+                                const float *projections, int64_t proj_view_stride, float stride, uint32_t flags,
+                                float *volume, int64_t vol_stride_voxel, int64_t vol_stride_channel, int32_t *count,
+                                uint8_t *valid, int reserve_ctas, void *stream) {
     if (!grid_ok(grid) || !features || !volume || !count || !(stride > 0.0f)) return CNRMA_ERR_ARG;
+    if (box && !box_ok(grid, box)) return CNRMA_ERR_ARG;
     if (!projections && features->views > 0) return CNRMA_ERR_ARG;
     if (flags & ~(CNRMA_AGG_ACCUMULATE | CNRMA_AGG_MEAN | CNRMA_AGG_COUNT_F32)) return CNRMA_ERR_ARG;
     const int fs = features_ok(features, true, (flags & CNRMA_AGG_ACCUMULATE) != 0);
@@ -99,7 +108,7 @@ int cnrma_aggregate_views(const cnrma_grid *grid, const cnrma_features *features
     // Tuning knob (DESIGN.md "K_A"): cap on the bytes of a feature row gathered per channel pass (<= 1024).
     int max_chunk_vecs = 0;
     if (const char *env = std::getenv("CNRMA_AGG_CHUNK_BYTES")) max_chunk_vecs = std::atoi(env);
-    const GridDev g = to_dev(*grid);
+    const GridDev g = box ? to_dev_box(*grid, *box) : to_dev(*grid);
     // Views go out in batches that accumulate into the volume in view order (the fp32 chain of the reference's
     // `self.volume + volume` loop is unchanged).  Short rows with many views are split into batches the list kernel
     // can serve (DESIGN.md "K_A'"): the extra read-modify-write of the volume costs far less than the per-row
@@ -122,11 +131,57 @@ int cnrma_aggregate_views(const cnrma_grid *grid, const cnrma_features *features
         const cudaError_t e = run_aggregate_views(g, *features, v0, nv, projections + (int64_t)v0 * proj_view_stride,
                                                   proj_view_stride, stride, fl, volume, vol_stride_voxel,
                                                   vol_stride_channel, count, valid, max_chunk_vecs,
-                                                  static_cast<cudaStream_t>(stream));
+                                                  static_cast<cudaStream_t>(stream), nullptr, reserve_ctas);
         if (e != cudaSuccess) return fail_cuda(e);
     }
     return CNRMA_OK;
 }
+
+int cnrma_aggregate_views(const cnrma_grid *grid, const cnrma_features *features, const float *projections,
+                          int64_t proj_view_stride, float stride, uint32_t flags, float *volume,
+                          int64_t vol_stride_voxel, int64_t vol_stride_channel, int32_t *count, uint8_t *valid,
+                          void *stream) {
+    return aggregate_views_impl(grid, nullptr, features, projections, proj_view_stride, stride, flags, volume,
+                                vol_stride_voxel, vol_stride_channel, count, valid, 0, stream);
+}
+
+int cnrma_aggregate_views_box(const cnrma_grid *grid, const cnrma_box *box, const cnrma_features *features,
+                              const float *projections, int64_t proj_view_stride, float stride, uint32_t flags,
+                              float *volume, int64_t vol_stride_voxel, int64_t vol_stride_channel, int32_t *count,
+                              uint8_t *valid, int reserve_ctas, void *stream) {
+    if (!box || reserve_ctas < 0) return CNRMA_ERR_ARG;
+    return aggregate_views_impl(grid, box, features, projections, proj_view_stride, stride, flags, volume,
+                                vol_stride_voxel, vol_stride_channel, count, valid, reserve_ctas, stream);
+}
+
+int cnrma_mark_rows(const cnrma_grid *grid, const cnrma_box *box, const float *projections, int64_t proj_view_stride,
+                    int views, float stride, int height, int width, uint32_t *bitmap, void *stream) {
+    if (!grid_ok(grid) || !box_ok(grid, box) || !projections || !bitmap || views <= 0 || height <= 0 || width <= 0 ||
+        !(stride > 0.0f))
+        return CNRMA_ERR_ARG;
+    if ((int64_t)height * width >= ((int64_t)1 << 30)) return CNRMA_ERR_UNSUPPORTED;
+    const int d = device_ok();
+    if (d != CNRMA_OK) return d;
+    const cudaError_t e = run_mark_rows(to_dev_box(*grid, *box), projections, proj_view_stride, views, stride, height,
+                                        width, bitmap, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
+}
+
+int cnrma_pull_rows(const uint32_t *bitmap, int views, int height, int width, int row_bytes, const void *src,
+                    int64_t src_view_stride, void *dst, int64_t dst_view_stride, int ctas, void *stream) {
+    if (!bitmap || !src || !dst || views <= 0 || height <= 0 || width <= 0 || ctas < 0) return CNRMA_ERR_ARG;
+    if (row_bytes < 16 || row_bytes % 16 != 0 || row_bytes > 8192) return CNRMA_ERR_LAYOUT;
+    if (reinterpret_cast<uintptr_t>(src) % 16 != 0 || reinterpret_cast<uintptr_t>(dst) % 16 != 0 ||
+        src_view_stride % 16 != 0 || dst_view_stride % 16 != 0)
+        return CNRMA_ERR_LAYOUT;
+    const int d = device_ok();
+    if (d != CNRMA_OK) return d;
+    const cudaError_t e = run_pull_rows(bitmap, views, height, width, row_bytes, src, src_view_stride, dst, dst_view_stride,
+                                        ctas, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
+}
+
+int cnrma_pull_default_ctas(void) { return pull_default_ctas(); }
 
 int cnrma_aggregate_views_bilinear(const cnrma_grid *grid, const cnrma_features *features, const float *projections,
                                    int64_t proj_view_stride, float stride, uint32_t flags, float *volume, int32_t *count,

@@ -25,10 +25,17 @@ struct GridDev {
     int nx, ny, nz;
     float vs;
     float ox, oy, oz;
+    int x0, y0, z0;   // Stage A forward on a box of the grid: (nx, ny, nz) are the box's extents, (x0, y0, z0) its first voxel
 };
 
 static inline GridDev to_dev(const cnrma_grid &g) {
-    return GridDev{g.nx, g.ny, g.nz, g.voxel_size, g.origin[0], g.origin[1], g.origin[2]};
+    return GridDev{g.nx, g.ny, g.nz, g.voxel_size, g.origin[0], g.origin[1], g.origin[2], 0, 0, 0};
+}
+
+// The sub-volume [lo, lo + dim) of `g`: world coordinates are formed from the GLOBAL voxel index (float(i) * vs + origin,
+// two roundings, rm.py:48), so a box reproduces the bits of the full-grid pass; outputs are indexed inside the box.
+static inline GridDev to_dev_box(const cnrma_grid &g, const cnrma_box &b) {
+    return GridDev{b.dim[0], b.dim[1], b.dim[2], g.voxel_size, g.origin[0], g.origin[1], g.origin[2], b.lo[0], b.lo[1], b.lo[2]};
 }
 
 // torch.bmm([3|4]x4 @ 4xN) in fp32 == this FMA chain in k order (rm.py:51, :105-107).

@@ -21,11 +21,12 @@ cudaError_t run_project_views(const GridDev &g, const float *proj, int64_t proj_
 cudaError_t run_aggregate_views(const GridDev &g, const cnrma_features &f, int v0, int nv, const float *proj,
                                 int64_t proj_stride, float stride, uint32_t flags, float *volume, int64_t vsv,
                                 int64_t vsc, int32_t *count, uint8_t *valid, int max_chunk_bytes, cudaStream_t stream,
-                                const OutputRoute *route = nullptr);
+                                const OutputRoute *route = nullptr, int reserve_ctas = 0);
 bool list_kernel_supports(int V, int H, int W);
 cudaError_t run_aggregate_list(const GridDev &g, const cnrma_features &f, int v0, int nv, const float *proj,
                                int64_t proj_stride, float stride, uint32_t flags, float *volume, int64_t vsv, int64_t vsc,
-                               int32_t *count, uint8_t *valid, cudaStream_t stream, const OutputRoute *route = nullptr);
+                               int32_t *count, uint8_t *valid, cudaStream_t stream, const OutputRoute *route = nullptr,
+                               int reserve_ctas = 0);
 cudaError_t run_aggregate_bilinear(const GridDev &g, const cnrma_features &f, const float *proj, int64_t proj_stride,
                                    float stride, uint32_t flags, float *volume, int32_t *count, uint8_t *valid,
                                    cudaStream_t stream);
@@ -34,6 +35,13 @@ cudaError_t run_finalize_routed(const float *recv, int n_src, int slab, int row_
 cudaError_t run_selftest_count_division(int max_n, unsigned long long *mismatches, cudaStream_t stream);
 cudaError_t run_to_channels_last(const void *const *views_host, int views, int dtype, int C, int H, int W, int64_t sc,
                                  int64_t sy, int64_t sx, void *dst, cudaStream_t stream);
+
+// cnrma_exchange.cu
+cudaError_t run_mark_rows(const GridDev &box, const float *proj, int64_t proj_stride, int V, float stride, int H, int W,
+                          uint32_t *bitmap, cudaStream_t stream);
+cudaError_t run_pull_rows(const uint32_t *bitmap, int views, int H, int W, int row_bytes, const void *src, int64_t src_vs,
+                          void *dst, int64_t dst_vs, int ctas, cudaStream_t stream);
+int pull_default_ctas();
 
 // cnrma_stage_b.cu
 RmaWorkspace rma_workspace(int views, int height, int width, int grids, int mode, float threshold, int depth_points,

@@ -45,6 +45,7 @@ struct AggParams {
     int rows_cap;                 // row slots per warp buffer
     SweepOrder sweep;             // traversal order of the voxels
     int bilinear;                 // opt-in variant: four neighbouring rows per visible view
+    int reserve_ctas;             // host only: CTA slots left free for a kernel that runs beside this one
     OutputRoute route;            // view-sharded output over peer memory (n_owners == 0: plain output)
     const void *views[kMaxViewsPerLaunch];
 };
@@ -102,9 +103,9 @@ aggregate_views_kernel(const __grid_constant__ AggParams p) {
         sweep_voxel(p.sweep, it, vx, vy, vz);
         // voxel order of datasets/tsdf.py:24-29: flat = (x*ny + y)*nz + z
         const int vox = (vx * p.g.ny + vy) * p.g.nz + vz;
-        const float wx = world_coord(vx, p.g.vs, p.g.ox);
-        const float wy = world_coord(vy, p.g.vs, p.g.oy);
-        const float wz = world_coord(vz, p.g.vs, p.g.oz);
+        const float wx = world_coord(vx + p.g.x0, p.g.vs, p.g.ox);
+        const float wy = world_coord(vy + p.g.y0, p.g.vs, p.g.oy);
+        const float wz = world_coord(vz + p.g.z0, p.g.vs, p.g.oz);
 
         float acc[VPL][E];
         int cnt = 0;
@@ -297,7 +298,8 @@ static cudaError_t launch_agg(const AggParams &p, int chunks, cudaStream_t strea
         cache.smem = smem;
         cache.ctas = sms * per_sm;
     }
-    const int persistent = cache.ctas;
+    int persistent = cache.ctas - p.reserve_ctas;
+    if (persistent < 1) persistent = 1;
     const int needed = (p.nvox + (kAggThreads / kWarp) - 1) / (kAggThreads / kWarp);
     const dim3 grid(needed < persistent ? needed : persistent, chunks);
     kernel<<<grid, kAggThreads, smem, stream>>>(p);
@@ -346,7 +348,7 @@ static cudaError_t run_aggregate(const AggParams &p_in, int dtype, int max_chunk
 cudaError_t run_aggregate_views(const GridDev &g, const cnrma_features &f, int v0, int nv, const float *proj,
                                 int64_t proj_stride, float stride, uint32_t flags, float *volume, int64_t vsv,
                                 int64_t vsc, int32_t *count, uint8_t *valid, int max_chunk_bytes, cudaStream_t stream,
-                                const OutputRoute *route) {
+                                const OutputRoute *route, int reserve_ctas) {
     // Kernel choice (DESIGN.md "K_A"): rows of 512 bytes and more go through the TMA kernel below (DRAM-bound, deep
     // register-free gather queue); shorter rows -- and the finalise-only pass -- through the list kernel
     // (cnrma_stage_a_list.cu), whose lane <-> voxel projection needs a third of the instructions.
@@ -355,7 +357,8 @@ cudaError_t run_aggregate_views(const GridDev &g, const cnrma_features &f, int v
     bool use_list = ((row_bytes < 512 && nv <= kListViewsMax) || nv == 0) && !(flags & kAggBilinearInternal);
     if (const char *env = std::getenv("CNRMA_AGG_KERNEL")) use_list = (env[0] == 'l') && !(flags & kAggBilinearInternal);   // tuning aid: "list" / "tma"
     if (use_list && list_kernel_supports(nv, f.height, f.width))
-        return run_aggregate_list(g, f, v0, nv, proj, proj_stride, stride, flags, volume, vsv, vsc, count, valid, stream, route);
+        return run_aggregate_list(g, f, v0, nv, proj, proj_stride, stride, flags, volume, vsv, vsc, count, valid, stream, route,
+                                  reserve_ctas);
     AggParams p;
     p.g = g;
     p.V = nv;
@@ -386,6 +389,7 @@ cudaError_t run_aggregate_views(const GridDev &g, const cnrma_features &f, int v
     p.chunk_bytes = 0;
     p.rows_cap = 0;
     p.bilinear = (flags & kAggBilinearInternal) ? 1 : 0;
+    p.reserve_ctas = reserve_ctas > 0 ? reserve_ctas : 0;
     p.flags = flags & ~kAggBilinearInternal;
     p.sweep = make_sweep(g.nx, g.ny, g.nz, sweep_thickness(g.ny, g.nz, nv, row_bytes));
     return run_aggregate(p, f.dtype, max_chunk_bytes, stream);
@@ -444,8 +448,8 @@ __global__ void __launch_bounds__(256) project_views_kernel(GridDev g, const flo
     const int vy = vxy % g.ny;
     const int vx = vxy / g.ny;
     int px, py;
-    const bool ok = project_voxel(sP, 1, world_coord(vx, g.vs, g.ox), world_coord(vy, g.vs, g.oy),
-                                  world_coord(vz, g.vs, g.oz), H, W, px, py);
+    const bool ok = project_voxel(sP, 1, world_coord(vx + g.x0, g.vs, g.ox), world_coord(vy + g.y0, g.vs, g.oy),
+                                  world_coord(vz + g.z0, g.vs, g.oz), H, W, px, py);
     const int64_t o = (int64_t)view * nvox + vox;
     if (px_out) px_out[o] = px;
     if (py_out) py_out[o] = py;

@@ -37,6 +37,7 @@ struct ListParams {
     // uniform: the views are equally spaced in one allocation, so a list entry is the row's offset from views[0] in
     // 16-byte units (one multiply-add to decode); otherwise entries pack (view, py, px) and go through the pointer table
     int uniform;
+    int reserve_ctas;   // host only: CTA slots left free for a kernel that runs beside this one
     uint32_t view_stride16, stride_y16, stride_x16;
     const void *views[kMaxViewsPerLaunch];
 };
@@ -84,9 +85,9 @@ __global__ void __launch_bounds__(kListThreads) aggregate_views_list_kernel(cons
         int vx, vy, vz;
         sweep_voxel(p.sweep, active ? it : 0, vx, vy, vz);
         const int vox = (vx * p.g.ny + vy) * p.g.nz + vz;    // voxel order of datasets/tsdf.py:24-29
-        const float wx = world_coord(vx, p.g.vs, p.g.ox);
-        const float wy = world_coord(vy, p.g.vs, p.g.oy);
-        const float wz = world_coord(vz, p.g.vs, p.g.oz);
+        const float wx = world_coord(vx + p.g.x0, p.g.vs, p.g.ox);
+        const float wy = world_coord(vy + p.g.y0, p.g.vs, p.g.oy);
+        const float wz = world_coord(vz + p.g.z0, p.g.vs, p.g.oz);
         uint32_t *lst = my_lists + lane * p.lcap;
         int cnt = 0;
         for (int v = 0; v < p.V; ++v) {
@@ -223,7 +224,9 @@ static cudaError_t launch_list(const ListParams &p, int chunks, cudaStream_t str
     }
     const int units = (p.nvox + p.nb - 1) / p.nb;
     const int needed = (units + (kListThreads / kWarp) - 1) / (kListThreads / kWarp);
-    const dim3 grid(needed < cache.ctas ? needed : cache.ctas, chunks);
+    int persistent = cache.ctas - p.reserve_ctas;
+    if (persistent < 1) persistent = 1;
+    const dim3 grid(needed < persistent ? needed : persistent, chunks);
     kernel<<<grid, kListThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
@@ -245,7 +248,8 @@ bool list_kernel_supports(int V, int H, int W) { return V <= 4096 && H <= 1024 &
 
 cudaError_t run_aggregate_list(const GridDev &g, const cnrma_features &f, int v0, int nv, const float *proj,
                                int64_t proj_stride, float stride, uint32_t flags, float *volume, int64_t vsv, int64_t vsc,
-                               int32_t *count, uint8_t *valid, cudaStream_t stream, const OutputRoute *route) {
+                               int32_t *count, uint8_t *valid, cudaStream_t stream, const OutputRoute *route,
+                               int reserve_ctas) {
     const int esz = (f.dtype == CNRMA_BF16) ? 2 : 4;
     const int nvec = f.channels * esz / 16;
     // lanes per voxel: the largest power of two <= 32 dividing nvec; the rest as vectors per lane (<= 4) and chunks
@@ -277,6 +281,7 @@ cudaError_t run_aggregate_list(const GridDev &g, const cnrma_features &f, int v0
         p.vec_store = 1;
     }
     p.sweep = make_sweep(g.nx, g.ny, g.nz, sweep_thickness(g.ny, g.nz, nv, f.channels * esz));
+    p.reserve_ctas = reserve_ctas > 0 ? reserve_ctas : 0;
     p.lcap = nv | 1;                                      // odd: the lanes' list writes hit different banks
     int nb = 32;                                          // voxels per warp batch: lists must fit ~8 KB per warp
     while (nb > 1 && (size_t)nb * p.lcap * 4 > 8192) nb >>= 1;

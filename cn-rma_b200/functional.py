@@ -47,39 +47,64 @@ def _as_view_list(features):
 
 
 class _FeatureStack:
-    """Per-batch-element cnrma_features descriptors for a list of per-view [B,C,H,W] tensors.
+    """Per-batch-element cnrma_features descriptors for the views of a scene: a stacked [V,B,C,H,W] tensor (the
+    pointers are then computed from its strides, no per-view tensors are made) or a list of per-view [B,C,H,W] tensors.
 
     Keeps the tensors (and any channels-last copies) alive for as long as the descriptor is used."""
 
-    def __init__(self, views, need_vector_layout):
-        f0 = views[0]
+    def __init__(self, features, need_vector_layout):
+        stacked = isinstance(features, torch.Tensor)
+        if stacked:
+            if features.dim() != 5:
+                raise ValueError("features must be [V,B,C,H,W] or a sequence of [B,C,H,W]")
+            f0 = features[0]
+            self.V = features.shape[0]
+        else:
+            views = _as_view_list(features)
+            f0 = views[0]
+            self.V = len(views)
         if not f0.is_cuda:
             raise CnrmaError("features must be CUDA tensors: this path has no CPU implementation")
         if f0.dtype not in _DTYPES:
             raise CnrmaError(f"unsupported feature dtype {f0.dtype} (float32 or bfloat16)")
         self.device = f0.device
         self.dtype = f0.dtype
-        self.V = len(views)
         self.B, self.C, self.H, self.W = f0.shape
-        for f in views:
-            if f.shape != f0.shape or f.dtype != f0.dtype or f.device != f0.device:
-                raise ValueError("all views must share shape, dtype and device")
-        self.views = [f.detach() for f in views]
         e = 8 if self.dtype == torch.bfloat16 else 4
-        ok = self.C % e == 0 or not need_vector_layout
-        if not ok:
+        if need_vector_layout and self.C % e != 0:
             raise CnrmaError(f"channels must be a multiple of {e} for {self.dtype}")
-        strides = {f.stride()[1:] for f in self.views}
-        sc, sy, sx = next(iter(strides))
         esz = f0.element_size()
-        aligned = all(f.data_ptr() % 16 == 0 and (f.stride(0) * esz) % 16 == 0 for f in self.views)
+        if stacked:
+            self.views = None
+            self.keep = features.detach()
+            strides = {tuple(features.stride()[2:])}
+            ptr0, vstep = features.data_ptr(), features.stride(0) * esz
+            aligned = ptr0 % 16 == 0 and vstep % 16 == 0 and (features.stride(1) * esz) % 16 == 0
+        else:
+            for f in views:
+                if f.shape != f0.shape or f.dtype != f0.dtype or f.device != f0.device:
+                    raise ValueError("all views must share shape, dtype and device")
+            self.views = [f.detach() for f in views]
+            self.keep = self.views
+            strides = {f.stride()[1:] for f in self.views}
+            aligned = all(f.data_ptr() % 16 == 0 and (f.stride(0) * esz) % 16 == 0 for f in self.views)
+        sc, sy, sx = next(iter(strides))
         cl = len(strides) == 1 and sc == 1 and (not need_vector_layout or (sx % e == 0 and sy % e == 0 and aligned))
         if not cl:
+            if self.views is None:
+                self.views = [self.keep[v] for v in range(self.V)]
             self.views = self._to_channels_last()
-        self.sc, self.sy, self.sx = self.views[0].stride()[1:]
+            self.keep = self.views
+            stacked = False
         self.converted = not cl
-        self._base = [f.data_ptr() for f in self.views]
-        self._bstride = [f.stride(0) * esz for f in self.views]
+        if stacked:
+            self.sc, self.sy, self.sx = sc, sy, sx
+            self._base = [ptr0 + v * vstep for v in range(self.V)]
+            self._bstride = [features.stride(1) * esz] * self.V
+        else:
+            self.sc, self.sy, self.sx = self.views[0].stride()[1:]
+            self._base = [f.data_ptr() for f in self.views]
+            self._bstride = [f.stride(0) * esz for f in self.views]
 
     def _to_channels_last(self):
         lib = _lib.load()
@@ -244,7 +269,7 @@ def project_views(projections, voxel_dim, voxel_size, origin, stride, height, wi
 
 
 def aggregate_views(projections, features, voxel_dim, voxel_size, origin, stride, mean=True, out=None,
-                    accumulate=None, count_f32=False):
+                    accumulate=None, count_f32=False, box=None, reserve_ctas=0):
     """Fused Stage A: V x aggregate_2d_features (+ clear_3d_features when mean=True), rm.py:220-257.
 
     projections [V,B,3,4] un-scaled; features [V,B,C,H,W] or a sequence of [B,C,H,W].
@@ -253,15 +278,25 @@ def aggregate_views(projections, features, voxel_dim, voxel_size, origin, stride
     `out=(volume, count, valid)` supplies the buffers; with `accumulate` (default when `out` is given) the
     new views are added to the un-averaged sums / counts already there (rm.py:243-244 semantics) and
     `mean` finishes them.  `count_f32` stores the counts as float32 (exact below 2**24) so sums and counts
-    can share one fp32 all-reduce buffer (distributed.py)."""
+    can share one fp32 all-reduce buffer (distributed.py).  `box=(lo, dim)` restricts the pass to the voxels
+    [lo, lo + dim) of the grid: the outputs then have the box's extents, and every voxel gets the bits the full-grid
+    call gives it (the unit of work of the voxel-sharded and chunk-pipelined multi-GPU modes, distributed.py);
+    `reserve_ctas` leaves that many CTA slots to a kernel running beside this one."""
     lib = _lib.load()
-    fs = _FeatureStack(_as_view_list(features), need_vector_layout=True)
+    fs = _FeatureStack(features, need_vector_layout=True)
     device = fs.device
     P = _projections_device(projections, device)
     if P.shape[0] != fs.V or P.shape[1] != fs.B:
         raise ValueError("projections / features disagree on views or batch")
-    nx, ny, nz = (int(v) for v in voxel_dim)
     grid = _lib.make_grid(voxel_dim, voxel_size, _origin3(origin))
+    box_c = None
+    if box is not None:
+        lo, dim = box
+        if any(int(l) < 0 or int(d) <= 0 or int(l) + int(d) > int(n) for l, d, n in zip(lo, dim, voxel_dim)):
+            raise ValueError("box must lie inside the grid")
+        box_c = _lib.make_box(lo, dim)
+        voxel_dim = tuple(int(d) for d in dim)
+    nx, ny, nz = (int(v) for v in voxel_dim)
     flags = (_lib.AGG_MEAN if mean else 0) | (_lib.AGG_COUNT_F32 if count_f32 else 0)
     if out is None:
         buf = _lib.empty((fs.B, nx, ny, nz, fs.C), dtype=torch.float32, device=device)
@@ -273,19 +308,25 @@ def aggregate_views(projections, features, voxel_dim, voxel_size, origin, stride
         if accumulate is None or accumulate:
             flags |= _lib.AGG_ACCUMULATE
         _check_out(volume, count, fs.B, fs.C, nx, ny, nz, count_f32)
-    view_list = _as_view_list(features)
+    view_list = [features] if isinstance(features, torch.Tensor) else _as_view_list(features)
     with_grad = _needs_grad(view_list)
-    if with_grad and (out is not None or count_f32):
-        raise CnrmaError("autograd through aggregate_views needs the one-call form (no `out=` accumulation)")
+    if with_grad and (out is not None or count_f32 or box is not None):
+        raise CnrmaError("autograd through aggregate_views needs the one-call form (no `out=` accumulation, no box)")
     with torch.cuda.device(device):
         for b in range(fs.B):
             desc = fs.descriptor(b)
             vb = volume[b]
-            _lib.check(lib.cnrma_aggregate_views(C.byref(grid), C.byref(desc), C.c_void_p(P[0, b].data_ptr()),
-                                                 fs.B * 12, float(stride), flags, C.c_void_p(vb.data_ptr()),
-                                                 vb.stride(3), vb.stride(0), C.c_void_p(count[b].data_ptr()),
-                                                 C.c_void_p(valid[b].data_ptr()) if valid is not None else None,
-                                                 _stream(device)), "cnrma_aggregate_views")
+            tail = (C.c_void_p(vb.data_ptr()), vb.stride(3), vb.stride(0), C.c_void_p(count[b].data_ptr()),
+                    C.c_void_p(valid[b].data_ptr()) if valid is not None else None)
+            if box_c is None:
+                _lib.check(lib.cnrma_aggregate_views(C.byref(grid), C.byref(desc), C.c_void_p(P[0, b].data_ptr()),
+                                                     fs.B * 12, float(stride), flags, *tail, _stream(device)),
+                           "cnrma_aggregate_views")
+            else:
+                _lib.check(lib.cnrma_aggregate_views_box(C.byref(grid), C.byref(box_c), C.byref(desc),
+                                                         C.c_void_p(P[0, b].data_ptr()), fs.B * 12, float(stride), flags,
+                                                         *tail, int(reserve_ctas), _stream(device)),
+                           "cnrma_aggregate_views_box")
     if with_grad:
         inputs, stacked = _autograd_inputs(features, view_list)
         state = dict(shape=(fs.V, fs.B, fs.C, fs.H, fs.W), device=device, voxel_dim=(nx, ny, nz), grid=grid, P=P,
@@ -299,7 +340,7 @@ def aggregate_views_bilinear(projections, features, voxel_dim, voxel_size, origi
     """OPT-IN extra (not in the reference, which samples nearest): Stage A with bilinear sampling at the projected
     position, same validity mask / counts as aggregate_views.  Returns (volume, count, valid) in the same layouts."""
     lib = _lib.load()
-    fs = _FeatureStack(_as_view_list(features), need_vector_layout=True)
+    fs = _FeatureStack(features, need_vector_layout=True)
     device = fs.device
     P = _projections_device(projections, device)
     nx, ny, nz = (int(v) for v in voxel_dim)
@@ -321,6 +362,10 @@ def aggregate_views_bilinear(projections, features, voxel_dim, voxel_size, origi
 def _check_out(volume, count, B, Cc, nx, ny, nz, count_f32):
     if tuple(volume.shape) != (B, Cc, nx, ny, nz) or volume.dtype != torch.float32 or not volume.is_cuda:
         raise ValueError("out volume has the wrong shape, dtype or device")
+    # the kernel addresses voxel (x, y, z) at ((x*ny + y)*nz + z) * stride(4): the volume must be linear over the voxels
+    sz = volume.stride(4)
+    if (ny > 1 and volume.stride(3) != nz * sz) or (nx > 1 and volume.stride(2) != ny * nz * sz):
+        raise ValueError("out volume must be linearly addressable over (x, y, z)")
     if count.dtype != (torch.float32 if count_f32 else torch.int32) or count.numel() != B * nx * ny * nz \
             or not count.is_contiguous():
         raise ValueError("out count has the wrong shape or dtype")
@@ -542,9 +587,9 @@ def rma_points(projections, features, tsdf, voxel_dim, voxel_size, origin, strid
     returns.  A batch element with no kept sample yields an empty [0, .] tensor (the reference raises).
     `mean_hook(weight_sum, rows, device) -> float32 CUDA tensor [1]` overrides the divisor of rm.py:303."""
     _check_mode(mode, threshold, depth_points)
-    view_list = _as_view_list(features)
+    view_list = [features] if isinstance(features, torch.Tensor) else _as_view_list(features)
     with_grad = _needs_grad(view_list)
-    fs = _FeatureStack(view_list, need_vector_layout=False)
+    fs = _FeatureStack(features, need_vector_layout=False)
     device = fs.device
     if not isinstance(projections, torch.Tensor):
         projections = torch.stack(list(projections), dim=0)
@@ -614,7 +659,7 @@ def dense_rma(projections, features, tsdf, voxel_dim, voxel_size, origin, stride
     accumulates into existing buffers."""
     _check_mode(mode, threshold, depth_points)
     lib = _lib.load()
-    fs = _FeatureStack(_as_view_list(features), need_vector_layout=False)
+    fs = _FeatureStack(features, need_vector_layout=False)
     device = fs.device
     if not isinstance(projections, torch.Tensor):
         projections = torch.stack(list(projections), dim=0)
@@ -756,8 +801,7 @@ def rma_points_selected(projections, features, tsdf, voxel_dim, voxel_size, orig
     Returns (coords list of [Nsel,3], features list of [Nsel,C]) like switch_pointcloud."""
     _check_mode(mode, threshold, depth_points)
     lib = _lib.load()
-    view_list = _as_view_list(features)
-    fs = _FeatureStack(view_list, need_vector_layout=False)
+    fs = _FeatureStack(features, need_vector_layout=False)
     device = fs.device
     if not isinstance(projections, torch.Tensor):
         projections = torch.stack(list(projections), dim=0)

@@ -144,13 +144,13 @@ def room_depth_maps(k, poses, height, width, extent, rng=None, holes=0.02):
     return out
 
 
-def room_tsdf(voxel_dim, trunc_voxels=3.0):
+def room_tsdf(voxel_dim, trunc_voxels=3.0, walls=(0.15, 0.85)):
     """Box room: walls at 15 % / 85 % of the extent on every axis, truncation 3 voxels."""
     nx, ny, nz = voxel_dim
     gx, gy, gz = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
     d = np.full(voxel_dim, np.inf)
     for g, n in ((gx, nx), (gy, ny), (gz, nz)):
-        lo, hi = 0.15 * (n - 1), 0.85 * (n - 1)
+        lo, hi = walls[0] * (n - 1), walls[1] * (n - 1)
         d = np.minimum(d, np.minimum(g - lo, hi - g))      # >0 inside the room, in voxels
     sdf = -d / trunc_voxels                                # free space negative, behind walls positive
     tsdf = np.clip(sdf, -1.0, 1.0)
@@ -170,6 +170,12 @@ def make_scene(config="cfg2", seed=0, with_features=True, stride=4, **override):
     proj = ring_cameras(cfg["views"], cfg["height"], cfg["width"], stride, extent, rng)
     if cfg["tsdf"] == "random":
         tsdf = rng.uniform(-1.0, 1.0, size=(nx, ny, nz)).astype(np.float32)
+    elif cfg["tsdf"] == "room_var":
+        # the room, with seed-dependent wall positions and truncation width, so that the number of samples the
+        # march keeps (M) differs from scene to scene; its own generator: the other draws are those of "room"
+        r2 = np.random.default_rng(7777 + seed)
+        tsdf = room_tsdf((nx, ny, nz), trunc_voxels=float(r2.uniform(2.0, 4.5)),
+                         walls=(float(r2.uniform(0.10, 0.20)), float(r2.uniform(0.80, 0.90))))
     else:
         tsdf = room_tsdf((nx, ny, nz))
     feats = None

@@ -48,6 +48,12 @@ typedef struct cnrma_grid {
     float origin[3];
 } cnrma_grid;
 
+/* A box of the volume: voxels [lo, lo + dim) on every axis (cnrma_aggregate_views_box, cnrma_mark_rows). */
+typedef struct cnrma_box {
+    int32_t lo[3];
+    int32_t dim[3];
+} cnrma_box;
+
 /* A stack of per-view feature maps (the `features` argument of rm.py:21 / :220 / :260 / :687).
  * view_ptrs_host is a HOST array of `views` DEVICE pointers, one per view's [C,H,W] map, so views that
  * live in separate tensors need no concatenation.  Strides are in elements.  The gather kernels
@@ -111,6 +117,33 @@ int cnrma_aggregate_views(const cnrma_grid *grid, const cnrma_features *features
                           int64_t proj_view_stride, float stride, uint32_t flags, float *volume,
                           int64_t vol_stride_voxel, int64_t vol_stride_channel, int32_t *count, uint8_t *valid,
                           void *stream);
+
+/* cnrma_aggregate_views restricted to a box of the grid -- the unit of work of the voxel-sharded multi-GPU mode
+ * (every rank owns one box and lifts ALL views into it) and of chunk-pipelined collectives.
+ * World coordinates are formed from the global voxel indices, so every voxel gets the bits the full-grid call gives
+ * it.  volume / count / valid are the BOX's buffers: voxel (x, y, z) of the box at ((x*dim[1] + y)*dim[2] + z).
+ *   reserve_ctas  number of this kernel's CTA slots to leave free for a kernel that runs beside it (the row puller
+ *                 below); 0 = take the whole GPU. */
+int cnrma_aggregate_views_box(const cnrma_grid *grid, const cnrma_box *box, const cnrma_features *features,
+                              const float *projections, int64_t proj_view_stride, float stride, uint32_t flags,
+                              float *volume, int64_t vol_stride_voxel, int64_t vol_stride_channel, int32_t *count,
+                              uint8_t *valid, int reserve_ctas, void *stream);
+
+/* Voxel-sharded Stage A, the exchange step: a rank that owns `box` needs, from the views other ranks hold, only the
+ * feature rows its voxels project to.
+ *   cnrma_mark_rows  sets bit (pixel % 32) of bitmap[view * words + pixel / 32], words = ceil(H*W / 32), for every
+ *                    (view, pixel) some voxel of the box gathers (same projection arithmetic as the gather kernels,
+ *                    so the set is exact).  The caller zeroes `bitmap` first; bits are only ever set.
+ *   cnrma_pull_rows  copies the marked rows of `views` channels-last maps from `src` (view v at src + v*src_view_stride
+ *                    bytes; a PEER-MAPPED pointer in the multi-GPU use: the reads cross NVLink) to the same offsets of
+ *                    `dst` (local staging, dst + v*dst_view_stride), as TMA bulk copies global -> shared -> global in a
+ *                    two-stage pipeline per warp.  row_bytes = C * sizeof(element), a multiple of 16, <= 8192.
+ *                    ctas = 0 picks the default grid (cnrma_pull_default_ctas). */
+int cnrma_mark_rows(const cnrma_grid *grid, const cnrma_box *box, const float *projections, int64_t proj_view_stride,
+                    int views, float stride, int height, int width, uint32_t *bitmap, void *stream);
+int cnrma_pull_rows(const uint32_t *bitmap, int views, int height, int width, int row_bytes, const void *src,
+                    int64_t src_view_stride, void *dst, int64_t dst_view_stride, int ctas, void *stream);
+int cnrma_pull_default_ctas(void);
 
 /* OPT-IN extra, not a replacement of any reference function: Stage A with bilinear instead of nearest sampling
  * (BASELINE.json's north_star names a bilinear gather; the reference samples nearest and parity with it wins, so

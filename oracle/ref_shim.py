@@ -1,13 +1,14 @@
 """TEST INFRASTRUCTURE ONLY -- import shim for the *real* CN-RMA reference.
 
-Only usable where /root/reference is mounted (the build container).  It lets
-`oracle/make_golden.py` and `tests/test_oracle_vs_reference.py` import the
+Usable where /root/reference is mounted (the build container) or where `oracle/build_ref.py` has staged a copy of
+the reference's Python package under oracle/_ref (git-ignored; it travels to the GPU box with the snapshot, which is
+how bench.py's CPU legs time the reference itself there).  It lets
+`oracle/make_golden.py`, `tests/test_oracle_vs_reference.py` and `oracle/ref_runner.py` import the
 reference's `projects/mvsdetection/models/ray_marching.py` unmodified by
 registering stub modules for the third-party packages that file imports at
 module scope (mmcv / mmdet / mmdet3d / MinkowskiEngine / open3d / skimage /
 trimesh) -- none of which the hot path (ray_marching.py:21-111, :200-307,
-:687-956) actually uses.  Nothing here is on the product path, and nothing
-here travels to the GPU box (the reference tree is not shipped).
+:687-956) actually uses.  Nothing here is on the product path.
 """
 import importlib
 import os
@@ -15,7 +16,17 @@ import sys
 import types
 from unittest import mock
 
-REFERENCE_ROOT = os.environ.get("CNRMA_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    for cand in (os.environ.get("CNRMA_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "projects", "mvsdetection")):
+            return cand
+    return os.environ.get("CNRMA_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _find_root()
 
 _STUBS = [
     "open3d", "MinkowskiEngine", "MinkowskiEngine.modules", "MinkowskiEngine.modules.resnet_block",

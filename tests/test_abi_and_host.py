@@ -99,3 +99,34 @@ def test_synthetic_scene_shapes():
     assert sc.voxel_views == 10_240_000 and sc.ray_steps == 288_000_000
     assert sc.projections.shape == (50, 3, 4) and sc.tsdf.shape == (80, 80, 32)
     assert np.abs(sc.tsdf).max() <= 1.05
+
+
+def test_box_shards_tile_the_grid():
+    for dim, w in [((160, 160, 64), 2), ((160, 160, 64), 4), ((160, 160, 64), 8), ((20, 20, 8), 8), ((13, 10, 7), 3),
+                   ((13, 10, 7), 6), ((80, 80, 32), 16), ((5, 4, 3), 1)]:
+        seen = np.zeros(dim, np.int32)
+        for r in range(w):
+            lo, bd = D.box_shard(dim, r, w)
+            seen[tuple(slice(l, l + d) for l, d in zip(lo, bd))] += 1
+        assert (seen == 1).all(), (dim, w)
+        gx, gy, gz = D.default_splits(w)
+        assert gx * gy * gz == w
+    assert D.default_splits(2) == (1, 1, 2) and D.default_splits(4) == (2, 1, 2) and D.default_splits(8) == (2, 2, 2)
+    with pytest.raises(ValueError):
+        D.box_shard((4, 4, 1), 0, 2)                  # the default cut for two ranks is along z
+    assert D.box_shard((4, 4, 1), 1, 2, splits=(2, 1, 1)) == ((2, 0, 0), (2, 4, 1))
+    for nx, parts in [(160, 4), (7, 3), (3, 5)]:
+        ch = D.x_chunks(nx, parts)
+        assert ch[0][0] == 0 and ch[-1][1] == nx and all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
+        assert all(b > a for a, b in ch)
+
+
+def test_box_struct_layout_and_reference_staging():
+    assert C.sizeof(_lib.Box) == 24 and _lib.Box.dim.offset == 12
+    import build_ref
+    import ref_shim
+    # wherever the reference tree is mounted the staged copy is complete; elsewhere the stage step is a no-op
+    if os.path.isdir("/root/reference/projects/mvsdetection"):
+        assert build_ref.stage()
+        assert os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "projects", "mvsdetection", "models", "ray_marching.py"))
+    assert ref_shim.available() == os.path.isdir(os.path.join(ref_shim.REFERENCE_ROOT, "projects", "mvsdetection"))
