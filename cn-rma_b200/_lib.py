@@ -21,6 +21,7 @@ OK = 0
 F32, BF16 = 0, 1
 AGG_ACCUMULATE, AGG_MEAN, AGG_COUNT_F32 = 1, 2, 4
 MARCH_NEUS, MARCH_DEPTH = 0, 1
+PULL_LSU = 0x10000
 
 
 class CnrmaError(RuntimeError):
@@ -111,9 +112,9 @@ _SIGNATURES = {
                                             C.c_float, C.c_uint32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                             C.c_int, C.c_void_p]),
     "cnrma_mark_rows": (C.c_int, [C.POINTER(Grid), C.POINTER(Box), C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_int, C.c_int,
-                                  C.c_void_p, C.c_void_p]),
-    "cnrma_pull_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
-                                  C.c_int, C.c_void_p]),
+                                  C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
+    "cnrma_pull_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p,
+                                  C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "cnrma_pull_default_ctas": (C.c_int, []),
     "cnrma_aggregate_views_bilinear": (C.c_int, [C.POINTER(Grid), C.POINTER(Features), C.c_void_p, C.c_int64, C.c_float,
                                                  C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -152,9 +153,11 @@ _SIGNATURES = {
                                     C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "cnrma_rma_fill_selected": (C.c_int, [C.POINTER(Grid), C.c_void_p, C.POINTER(Features), C.c_int, C.c_float, C.c_int,
                                           C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
-                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "cnrma_sample_workspace_bytes": (C.c_int, [C.POINTER(C.c_size_t)]),
     "cnrma_sample_mask": (C.c_int, [C.c_int64, C.c_int64, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "cnrma_sample_mask_for_result": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p,
+                                               C.c_void_p]),
     "cnrma_tsdf_integrate": (C.c_int, [C.POINTER(Grid), C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_void_p),
                                        C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_float,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -178,7 +181,7 @@ def load():
                 fn = getattr(lib, name)
                 fn.restype = res
                 fn.argtypes = args
-            if lib.cnrma_abi_version() != 1:
+            if lib.cnrma_abi_version() != 2:
                 raise CnrmaError("libcnrma_b200.so ABI version mismatch")
             _lib = lib
     return _lib

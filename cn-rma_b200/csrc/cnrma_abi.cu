@@ -155,29 +155,35 @@ int cnrma_aggregate_views_box(const cnrma_grid *grid, const cnrma_box *box, cons
 }
 
 int cnrma_mark_rows(const cnrma_grid *grid, const cnrma_box *box, const float *projections, int64_t proj_view_stride,
-                    int views, float stride, int height, int width, uint32_t *bitmap, void *stream) {
+                    int views, float stride, int height, int width, uint32_t *bitmap, int parts, int64_t part_stride,
+                    void *stream) {
     if (!grid_ok(grid) || !box_ok(grid, box) || !projections || !bitmap || views <= 0 || height <= 0 || width <= 0 ||
-        !(stride > 0.0f))
+        !(stride > 0.0f) || parts < 1 || parts > 16 || parts > box->dim[0] || (parts > 1 && part_stride <= 0))
         return CNRMA_ERR_ARG;
     if ((int64_t)height * width >= ((int64_t)1 << 30)) return CNRMA_ERR_UNSUPPORTED;
     const int d = device_ok();
     if (d != CNRMA_OK) return d;
     const cudaError_t e = run_mark_rows(to_dev_box(*grid, *box), projections, proj_view_stride, views, stride, height,
-                                        width, bitmap, static_cast<cudaStream_t>(stream));
+                                        width, bitmap, parts, part_stride, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
 }
 
-int cnrma_pull_rows(const uint32_t *bitmap, int views, int height, int width, int row_bytes, const void *src,
-                    int64_t src_view_stride, void *dst, int64_t dst_view_stride, int ctas, void *stream) {
-    if (!bitmap || !src || !dst || views <= 0 || height <= 0 || width <= 0 || ctas < 0) return CNRMA_ERR_ARG;
+int cnrma_pull_rows(const uint32_t *bitmap, uint32_t *done, int views, int height, int width, int row_bytes,
+                    const void *const *src_view_ptrs_host, void *dst, int64_t dst_view_stride, int ctas, uint32_t *work,
+                    int first_view, void *stream) {
+    if (!bitmap || !src_view_ptrs_host || !dst || views <= 0 || height <= 0 || width <= 0 || ctas < 0 || first_view < 0 ||
+        first_view >= views)
+        return CNRMA_ERR_ARG;
+    if (views > kMaxViewsPerLaunch) return CNRMA_ERR_UNSUPPORTED;
     if (row_bytes < 16 || row_bytes % 16 != 0 || row_bytes > 8192) return CNRMA_ERR_LAYOUT;
-    if (reinterpret_cast<uintptr_t>(src) % 16 != 0 || reinterpret_cast<uintptr_t>(dst) % 16 != 0 ||
-        src_view_stride % 16 != 0 || dst_view_stride % 16 != 0)
-        return CNRMA_ERR_LAYOUT;
+    if (reinterpret_cast<uintptr_t>(dst) % 16 != 0 || dst_view_stride % 16 != 0) return CNRMA_ERR_LAYOUT;
+    for (int v = 0; v < views; ++v)
+        if (!src_view_ptrs_host[v] || reinterpret_cast<uintptr_t>(src_view_ptrs_host[v]) % 16 != 0) return CNRMA_ERR_LAYOUT;
     const int d = device_ok();
     if (d != CNRMA_OK) return d;
-    const cudaError_t e = run_pull_rows(bitmap, views, height, width, row_bytes, src, src_view_stride, dst, dst_view_stride,
-                                        ctas, static_cast<cudaStream_t>(stream));
+    const cudaError_t e = run_pull_rows(bitmap, done, views, height, width, row_bytes, src_view_ptrs_host, dst,
+                                        dst_view_stride, ctas & 0xFFFF, work, first_view, (ctas >> 16) & 1,
+                                        static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
 }
 
@@ -315,7 +321,8 @@ int cnrma_rma_march(const cnrma_grid *grid, const float *pinv, int views, int he
 static int fill_common(const cnrma_grid *grid, const float *pinv, const cnrma_features *features, int grids,
                        float t_one, int mode, float threshold, int depth_points, const void *workspace, int normalize,
                        const float *mean, float *rows, int64_t row_stride, int64_t capacity, float *wsum, float *wtot,
-                       const uint8_t *sel_mask, const int32_t *sel_prefix, const float *sel_off_host, void *stream) {
+                       const uint8_t *sel_mask, const int32_t *sel_prefix, const float *sel_off_host, int64_t sel_rows,
+                       void *stream) {
     if (!grid_ok(grid) || !pinv || !workspace) return CNRMA_ERR_ARG;
     const int fs = features_ok(features, false);
     if (fs != CNRMA_OK) return fs;
@@ -325,7 +332,7 @@ static int fill_common(const cnrma_grid *grid, const float *pinv, const cnrma_fe
     const RmaWorkspace ws = rma_workspace(features->views, features->height, features->width, grids, mode, threshold,
                                           depth_points);
     const cudaError_t e = run_fill(to_dev(*grid), pinv, *features, t_one, mode, workspace, ws, normalize, mean, rows,
-                                   row_stride, capacity, wsum, wtot, sel_mask, sel_prefix, sel_off_host,
+                                   row_stride, capacity, wsum, wtot, sel_mask, sel_prefix, sel_off_host, sel_rows,
                                    static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
 }
@@ -342,21 +349,22 @@ int cnrma_rma_fill(const cnrma_grid *grid, const float *pinv, const cnrma_featur
     if (rows_host == 0 || capacity == 0) return CNRMA_OK;
     const float *mean_ptr = mean ? mean : &result->mean;
     return fill_common(grid, pinv, features, grids, t_one, mode, threshold, depth_points, workspace, normalize,
-                       mean_ptr, rows, row_stride, capacity, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+                       mean_ptr, rows, row_stride, capacity, nullptr, nullptr, nullptr, nullptr, nullptr, 0, stream);
 }
 
 int cnrma_rma_fill_selected(const cnrma_grid *grid, const float *pinv, const cnrma_features *features, int grids,
                             float t_one, int mode, float threshold, int depth_points, const void *workspace,
                             const cnrma_rma_result *result, int normalize, const float *mean, const uint8_t *mask,
-                            const int32_t *prefix, const float *offset_host, float *rows, int64_t row_stride,
-                            int64_t capacity, void *stream) {
-    if (!rows || !result || !mask || !prefix || !offset_host || capacity < 0 || !features) return CNRMA_ERR_ARG;
+                            const int32_t *prefix, int64_t mask_rows, const float *offset_host, float *rows,
+                            int64_t row_stride, int64_t capacity, void *stream) {
+    if (!rows || !result || !mask || !prefix || !offset_host || capacity < 0 || mask_rows < 0 || !features)
+        return CNRMA_ERR_ARG;
     const int cols = features->channels + (normalize ? 3 : 4);
     if (row_stride < cols) return CNRMA_ERR_ARG;
     if (capacity == 0) return CNRMA_OK;
     const float *mean_ptr = mean ? mean : &result->mean;
     return fill_common(grid, pinv, features, grids, t_one, mode, threshold, depth_points, workspace, normalize,
-                       mean_ptr, rows, row_stride, capacity, nullptr, nullptr, mask, prefix, offset_host, stream);
+                       mean_ptr, rows, row_stride, capacity, nullptr, nullptr, mask, prefix, offset_host, mask_rows, stream);
 }
 
 int cnrma_handoff_workspace_bytes(int64_t rows, size_t *bytes) {
@@ -394,7 +402,7 @@ int cnrma_rma_scatter(const cnrma_grid *grid, const float *pinv, const cnrma_fea
                       float *wtot, void *stream) {
     if (!wsum || !wtot) return CNRMA_ERR_ARG;
     return fill_common(grid, pinv, features, grids, t_one, mode, threshold, depth_points, workspace, 0, nullptr,
-                       nullptr, 0, 0, wsum, wtot, nullptr, nullptr, nullptr, stream);
+                       nullptr, 0, 0, wsum, wtot, nullptr, nullptr, nullptr, 0, stream);
 }
 
 int cnrma_aggregate_views_backward(const cnrma_grid *grid, const cnrma_features *grad_features, const float *projections,
@@ -446,6 +454,20 @@ int cnrma_sample_mask(int64_t rows, int64_t keep, uint64_t seed, void *workspace
     const int d = device_ok();
     if (d != CNRMA_OK) return d;
     const cudaError_t e = run_sample_mask(rows, keep, seed, workspace, mask, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
+}
+
+int cnrma_sample_mask_for_result(const cnrma_rma_result *result, int64_t capacity, int64_t keep, uint64_t seed,
+                                 void *workspace, size_t workspace_bytes, uint8_t *mask, void *stream) {
+    if (!result || !workspace || !mask || capacity < 0 || keep < 0) return CNRMA_ERR_ARG;
+    if (capacity >= ((int64_t)1 << 27)) return CNRMA_ERR_UNSUPPORTED;
+    if (workspace_bytes < sample_workspace_bytes()) return CNRMA_ERR_CAPACITY;
+    if (reinterpret_cast<uintptr_t>(workspace) % 8 != 0) return CNRMA_ERR_LAYOUT;
+    const int d = device_ok();
+    if (d != CNRMA_OK) return d;
+    static_assert(sizeof(long long) == sizeof(int64_t), "rows is read as long long");
+    const cudaError_t e = run_sample_mask(capacity, keep, seed, workspace, mask, static_cast<cudaStream_t>(stream),
+                                          reinterpret_cast<const long long *>(&result->rows));
     return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
 }
 

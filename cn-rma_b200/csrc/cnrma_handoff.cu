@@ -167,14 +167,36 @@ __device__ __forceinline__ unsigned long long sample_key(unsigned long long seed
     return (z & 0xFFFFFFFF00000000ull) | i;
 }
 
-__global__ void __launch_bounds__(256) sample_hist_kernel(unsigned long long seed, unsigned int n, SampleState *st) {
+// The row count either comes from the host (`n`) or, for the sync-free hand-off, from the march's result block in
+// device memory (`n_dev`, clamped to the `n` rows the buffers hold).
+__device__ __forceinline__ unsigned int sample_rows(unsigned int n, const long long *n_dev) {
+    if (n_dev == nullptr) return n;
+    const long long m = *n_dev;
+    return m < 0 ? 0u : (m < (long long)n ? (unsigned int)m : n);
+}
+
+__global__ void __launch_bounds__(256) sample_hist_kernel(unsigned long long seed, unsigned int n, const long long *n_dev,
+                                                          SampleState *st) {
+    n = sample_rows(n, n_dev);
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) atomicAdd(&st->hist[sample_key(seed, i) >> 48], 1u);
 }
 
-__global__ void __launch_bounds__(1024) sample_find_bin_kernel(unsigned int k, SampleState *st) {
+__global__ void __launch_bounds__(1024) sample_find_bin_kernel(unsigned int k, unsigned int n, const long long *n_dev,
+                                                               SampleState *st) {
     __shared__ unsigned int s[1024];
     const int t = threadIdx.x;
+    n = sample_rows(n, n_dev);
+    if (k >= n) {                       // nothing to drop (only reachable with a device-side row count): keep every row
+        if (t == 0) {
+            st->threshold = ~0ull;
+            st->bin = kSampleBins;      // no key lives there: collect / threshold become no-ops
+            st->below = 0;
+            st->ncand = 0;
+            st->overflow = 0;
+        }
+        return;
+    }
     unsigned int sum = 0;
     for (int b = t * 64; b < t * 64 + 64; ++b) sum += st->hist[b];
     s[t] = sum;
@@ -203,7 +225,9 @@ __global__ void __launch_bounds__(1024) sample_find_bin_kernel(unsigned int k, S
     }
 }
 
-__global__ void __launch_bounds__(256) sample_collect_kernel(unsigned long long seed, unsigned int n, SampleState *st) {
+__global__ void __launch_bounds__(256) sample_collect_kernel(unsigned long long seed, unsigned int n, const long long *n_dev,
+                                                             SampleState *st) {
+    n = sample_rows(n, n_dev);
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned long long key = sample_key(seed, i);
@@ -216,6 +240,7 @@ __global__ void __launch_bounds__(256) sample_collect_kernel(unsigned long long 
 
 __global__ void __launch_bounds__(1024) sample_threshold_kernel(unsigned int k, SampleState *st) {
     // the (k - below)-th smallest key of the boundary bin: rank by counting (a few hundred keys)
+    if (st->bin >= (unsigned int)kSampleBins) return;   // every row is kept (see sample_find_bin_kernel)
     const unsigned int m = min(st->ncand, (unsigned int)kSampleCand);
     const unsigned int want = k - st->below;    // 1-based rank inside the bin
     for (unsigned int a = threadIdx.x; a < m; a += blockDim.x) {
@@ -226,28 +251,30 @@ __global__ void __launch_bounds__(1024) sample_threshold_kernel(unsigned int k, 
     }
 }
 
-__global__ void __launch_bounds__(256) sample_mask_kernel(unsigned long long seed, unsigned int n, const SampleState *st,
-                                                          uint8_t *__restrict__ mask) {
+__global__ void __launch_bounds__(256) sample_mask_kernel(unsigned long long seed, unsigned int cap, const long long *n_dev,
+                                                          const SampleState *st, uint8_t *__restrict__ mask) {
+    const unsigned int n = sample_rows(cap, n_dev);
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) mask[i] = (uint8_t)(sample_key(seed, i) <= st->threshold);
+    if (i < cap) mask[i] = (uint8_t)(i < n && sample_key(seed, i) <= st->threshold);   // rows beyond the count: dropped
 }
 
 size_t sample_workspace_bytes() { return (sizeof(SampleState) + 255) / 256 * 256; }
 
+// n: the number of rows (n_dev == nullptr) or the capacity of `mask` when the row count is read from *n_dev.
 cudaError_t run_sample_mask(int64_t n, int64_t k, unsigned long long seed, void *workspace, uint8_t *mask,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, const long long *n_dev) {
     if (n == 0) return cudaSuccess;
-    if (k >= n) return cudaMemsetAsync(mask, 1, (size_t)n, stream);
+    if (n_dev == nullptr && k >= n) return cudaMemsetAsync(mask, 1, (size_t)n, stream);
     if (k <= 0) return cudaMemsetAsync(mask, 0, (size_t)n, stream);
     SampleState *st = static_cast<SampleState *>(workspace);
     cudaError_t err = cudaMemsetAsync(st->hist, 0, sizeof(st->hist), stream);
     if (err != cudaSuccess) return err;
     const unsigned int blocks = (unsigned int)((n + 255) / 256);
-    sample_hist_kernel<<<blocks, 256, 0, stream>>>(seed, (unsigned int)n, st);
-    sample_find_bin_kernel<<<1, 1024, 0, stream>>>((unsigned int)k, st);
-    sample_collect_kernel<<<blocks, 256, 0, stream>>>(seed, (unsigned int)n, st);
-    sample_threshold_kernel<<<1, 1024, 0, stream>>>((unsigned int)k, st);
-    sample_mask_kernel<<<blocks, 256, 0, stream>>>(seed, (unsigned int)n, st, mask);
+    sample_hist_kernel<<<blocks, 256, 0, stream>>>(seed, (unsigned int)n, n_dev, st);
+    sample_find_bin_kernel<<<1, 1024, 0, stream>>>((unsigned int)(k < n ? k : n), (unsigned int)n, n_dev, st);
+    sample_collect_kernel<<<blocks, 256, 0, stream>>>(seed, (unsigned int)n, n_dev, st);
+    sample_threshold_kernel<<<1, 1024, 0, stream>>>((unsigned int)(k < n ? k : n), st);
+    sample_mask_kernel<<<blocks, 256, 0, stream>>>(seed, (unsigned int)n, n_dev, st, mask);
     return cudaGetLastError();
 }
 

@@ -38,9 +38,10 @@ cudaError_t run_to_channels_last(const void *const *views_host, int views, int d
 
 // cnrma_exchange.cu
 cudaError_t run_mark_rows(const GridDev &box, const float *proj, int64_t proj_stride, int V, float stride, int H, int W,
-                          uint32_t *bitmap, cudaStream_t stream);
-cudaError_t run_pull_rows(const uint32_t *bitmap, int views, int H, int W, int row_bytes, const void *src, int64_t src_vs,
-                          void *dst, int64_t dst_vs, int ctas, cudaStream_t stream);
+                          uint32_t *bitmap, int parts, int64_t part_stride, cudaStream_t stream);
+cudaError_t run_pull_rows(const uint32_t *bitmap, uint32_t *done, int views, int H, int W, int row_bytes,
+                          const void *const *src_views_host, void *dst, int64_t dst_vs, int ctas, unsigned int *work,
+                          int first_view, int use_lsu, cudaStream_t stream);
 int pull_default_ctas();
 
 // cnrma_stage_b.cu
@@ -52,7 +53,7 @@ cudaError_t run_march(const GridDev &g, const float *pinv, int V, int H, int W, 
 cudaError_t run_fill(const GridDev &g, const float *pinv, const cnrma_features &f, float t_one, int mode,
                      const void *workspace, const RmaWorkspace &ws, int normalize, const float *mean, float *rows,
                      int64_t row_stride, int64_t capacity, float *wsum, float *wtot, const uint8_t *sel_mask,
-                     const int32_t *sel_prefix, const float *sel_off_host, cudaStream_t stream);
+                     const int32_t *sel_prefix, const float *sel_off_host, int64_t sel_rows, cudaStream_t stream);
 cudaError_t run_ray_parameters(const float *pinv, int V, int H, int W, float *o, float *d, cudaStream_t stream);
 cudaError_t run_expand(int64_t rays, int N, const void *workspace, const RmaWorkspace &ws, float *weights,
                        uint8_t *keep, cudaStream_t stream);
@@ -67,7 +68,7 @@ cudaError_t run_select_rows(const float *rows, int64_t row_stride, int cols, int
 
 size_t sample_workspace_bytes();
 cudaError_t run_sample_mask(int64_t n, int64_t k, unsigned long long seed, void *workspace, uint8_t *mask,
-                            cudaStream_t stream);
+                            cudaStream_t stream, const long long *n_dev = nullptr);
 
 constexpr uint32_t kAggBilinearInternal = 0x80000000u;   // library-internal flag bit: run_aggregate_views in bilinear mode
 constexpr int kListViewsMax = 96;     // the list kernel's per-voxel lists stop paying beyond this many views per launch

@@ -478,6 +478,7 @@ struct FillParams {
     int64_t capacity;     // rows the output buffer holds: rows beyond it are dropped (speculative launches)
     const uint8_t *sel_mask;     // optional hand-off selection: only rows with sel_mask[row] != 0 are written,
     const int32_t *sel_prefix;   // at row index sel_prefix[row], with sel_off added to x, y, z (rm.py:365, :380-402)
+    int64_t sel_rows;            // entries of sel_mask / sel_prefix: rows beyond them are dropped (a mask sized from a guess of M)
     float sel_off[3];
     float *wsum, *wtot;   // scatter variant
     const void *views[kMaxViewsPerLaunch];
@@ -571,7 +572,8 @@ __global__ void __launch_bounds__(kRayThreads) fill_rows_kernel(const __grid_con
                 const int64_t row_id = off + k0 + lane;
                 if (!SCATTER) {
                     dst_row = row_id;
-                    if (p.sel_mask != nullptr) dst_row = __ldg(p.sel_mask + row_id) ? (int64_t)__ldg(p.sel_prefix + row_id) : -1;
+                    if (p.sel_mask != nullptr)
+                        dst_row = (row_id < p.sel_rows && __ldg(p.sel_mask + row_id)) ? (int64_t)__ldg(p.sel_prefix + row_id) : -1;
                     if (dst_row >= p.capacity) dst_row = -1;
                 }
                 if (SCATTER || dst_row >= 0) {
@@ -908,8 +910,8 @@ __global__ void __launch_bounds__(kRayThreads) fill_rows_packed_kernel(const __g
     int64_t my_out0 = my_off;                                           // output row of my ray's first produced row
     if (SELECT) {
         my_keep = 0;
-        for (int k = 0; k < my_cnt; ++k) my_keep += __ldg(p.sel_mask + my_off + k) ? 1 : 0;
-        my_out0 = (my_cnt > 0) ? (int64_t)__ldg(p.sel_prefix + my_off) : 0;
+        for (int k = 0; k < my_cnt; ++k) my_keep += (my_off + k < p.sel_rows && __ldg(p.sel_mask + my_off + k)) ? 1 : 0;
+        my_out0 = (my_cnt > 0 && my_off < p.sel_rows) ? (int64_t)__ldg(p.sel_prefix + my_off) : 0;
     }
     const unsigned with_rows = __ballot_sync(0xffffffffu, my_cnt > 0);
     const int first_lane = with_rows ? (__ffs(with_rows) - 1) : 0;
@@ -986,7 +988,7 @@ __global__ void __launch_bounds__(kRayThreads) fill_rows_packed_kernel(const __g
             const int nk = min(32, cnt_all - k0);
             float wk = 0.0f, wraw = 0.0f, pos[3] = {0.0f, 0.0f, 0.0f};
             bool sel = lane < nk;
-            if (SELECT && sel) sel = __ldg(p.sel_mask + row0 + k0 + lane) != 0;
+            if (SELECT && sel) sel = (row0 + k0 + lane < p.sel_rows) && __ldg(p.sel_mask + row0 + k0 + lane) != 0;
             if (sel) {
                 wraw = __ldg(p.rec_w + (int64_t)(k0 + lane) * p.rays + ray);
                 const float fi = __ldg(p.rec_i + (int64_t)(k0 + lane) * p.rays + ray);
@@ -1164,7 +1166,7 @@ static cudaError_t launch_fill(FillParams &p, int dtype, const void *const *view
 cudaError_t run_fill(const GridDev &g, const float *pinv, const cnrma_features &f, float t_one, int mode,
                      const void *workspace, const RmaWorkspace &ws, int normalize, const float *mean, float *rows,
                      int64_t row_stride, int64_t capacity, float *wsum, float *wtot, const uint8_t *sel_mask,
-                     const int32_t *sel_prefix, const float *sel_off_host, cudaStream_t stream) {
+                     const int32_t *sel_prefix, const float *sel_off_host, int64_t sel_rows, cudaStream_t stream) {
     const unsigned char *base = static_cast<const unsigned char *>(workspace);
     FillParams p;
     p.g = g;
@@ -1185,6 +1187,7 @@ cudaError_t run_fill(const GridDev &g, const float *pinv, const cnrma_features &
     p.capacity = capacity;
     p.sel_mask = sel_mask;
     p.sel_prefix = sel_prefix;
+    p.sel_rows = sel_rows > 0 ? sel_rows : INT64_MAX;
     for (int a = 0; a < 3; ++a) p.sel_off[a] = sel_off_host ? sel_off_host[a] : 0.0f;
     p.wsum = wsum;
     p.wtot = wtot;

@@ -353,7 +353,7 @@ class ViewExchange:
     """Voxel-sharded Stage A of ONE scene whose views arrive sharded over the ranks (batch 1).
 
     Every rank owns one box of the volume (box_shard) and lifts ALL views into it, in view order -- the sums are
-    bit-identical to the single-GPU result (`overlap=False`) and nothing but feature rows crosses NVLink:
+    bit-identical to the single-GPU result and nothing but feature rows crosses NVLink:
 
       1. the producer (the 2D network) writes this rank's views into `local_features()`, a symmetric-memory buffer
          (torch.distributed._symmetric_memory) every peer can read;
@@ -361,10 +361,9 @@ class ViewExchange:
          kernels' own projection arithmetic) -- a fifth to a third of them for the boxes and cameras at hand;
       3. cnrma_pull_rows copies exactly those rows out of the peers' buffers into a local staging copy (TMA bulk copies
          through shared memory, on a side stream, one launch per peer so that every peer serves one reader at a time);
-      4. cnrma_aggregate_views_box gathers from the local views and the staged remote ones.
-         overlap=True   local views first, then each peer's views as soon as its rows are in: the pulls run beside the
-                        gather kernel, which leaves them their CTA slots.  Sums are regrouped (rotated view order): 1e-5.
-         overlap=False  one launch over all views in view order once every row is in: bit-identical to one GPU.
+      4. cnrma_aggregate_views_box gathers from the local views and the staged remote ones, all views in view order.
+         With overlap=True the box is served part by part: the rows of the next part arrive while the current one is
+         being gathered (the gather kernel leaves the puller its CTA slots).
 
     Returns this rank's box; all-gather the boxes if one rank needs the whole volume."""
 
@@ -382,11 +381,18 @@ class ViewExchange:
         self.peers = [self.hdl.get_buffer(q, shape, dtype) for q in range(self.world)]
         self.staging = torch.empty((self.V, self.H, self.W, self.C), dtype=dtype, device=self.device)
         self.words = (self.H * self.W + 31) // 32
-        self.bitmap = torch.zeros((self.V, self.words), dtype=torch.int32, device=self.device)
+        self._bm = torch.zeros((5, self.V, self.words), dtype=torch.int32, device=self.device)   # [0]: rows present
+        self.bitmap = self._bm[0]
         self.side = torch.cuda.Stream(device=self.device, priority=-1)
         self.row_bytes = self.C * self.local.element_size()
         self.view_bytes = self.H * self.W * self.row_bytes
         self._descs = {}
+        self._work = torch.zeros(16, dtype=torch.int32, device=self.device)      # one claim counter per part
+        import ctypes as C
+        ptrs = []
+        for q, (qlo, qhi) in enumerate(self.shards):                             # view v lives in its owner's buffer
+            ptrs += [self.peers[q][i].data_ptr() for i in range(qhi - qlo)]
+        self._owner_ptrs = (C.c_void_p * self.V)(*ptrs)
 
     def local_features(self):
         """This rank's views as a [v_local, 1, C, H, W] tensor (channels-last rows in symmetric memory) to write into."""
@@ -419,10 +425,18 @@ class ViewExchange:
         per_view[mlo:mhi] = 0
         return int(per_view.sum()) * self.row_bytes
 
-    def aggregate(self, projections, voxel_dim, voxel_size, origin, stride, mean=True, overlap=True, pull_ctas=0):
+    def aggregate(self, projections, voxel_dim, voxel_size, origin, stride, mean=True, overlap=False, parts=4, pull_ctas=0,
+                  pull_path=None, profile=None):
         """projections [V,1,3,4]: the cameras of ALL views (replicated; 48 bytes each).  The local views must already be
         in local_features() (written on the current stream).  Returns (lo, dim, volume [1,C,*dim], count int32
-        [1,1,*dim], valid bool) for this rank's box."""
+        [1,1,*dim], valid bool) for this rank's box -- bit-identical to the same voxels of a single-GPU call.
+
+        overlap=False  mark, pull everything, then one gather launch over the box.
+        overlap=True   the box is cut into `parts` x-ranges; the rows of part k+1 (those not already there) are pulled
+                       while part k is being gathered, and the gather kernel leaves the puller its CTA slots.
+        pull_path: "tma" (bulk copies through shared memory) or "lsu" (16-byte loads / stores through registers);
+                   default: "lsu" beside the gather kernel (overlap), "tma" alone.
+        profile: a dict that receives the device times (ms) of the phases of this call (host sync; for reports)."""
         import ctypes as C
         from . import _lib
         lib = _lib.load()
@@ -432,61 +446,85 @@ class ViewExchange:
             raise ValueError("projections must hold the cameras of all views of one scene: [V,1,3,4]")
         lo, dim = box_shard(voxel_dim, self.rank, self.world, self.splits)
         grid = _lib.make_grid(voxel_dim, voxel_size, F._origin3(origin))
-        box = _lib.make_box(lo, dim)
         main = torch.cuda.current_stream(dev)
-        mlo, mhi = self.shards[self.rank]
+        lsu = (pull_path or ("lsu" if overlap else "tma")) == "lsu"
+        if not pull_ctas and not overlap:
+            pull_ctas = 2 * lib.cnrma_pull_default_ctas()    # nothing runs beside the puller: one CTA per SM
+        pull_arg = (int(pull_ctas) & 0xFFFF) | (_lib.PULL_LSU if lsu else 0)
         order = [(self.rank + k) % self.world for k in range(1, self.world)]     # every peer serves one reader at a time
         order = [q for q in order if self.shards[q][1] > self.shards[q][0]]
+        bx, by, bz = dim
+        xparts = x_chunks(bx, max(1, min(int(parts), bx, 16))) if (overlap and order) else [(0, bx)]
+        if self._bm.shape[0] < len(xparts) + 1:
+            self._bm = torch.zeros((len(xparts) + 1, self.V, self.words), dtype=torch.int32, device=dev)
+        done = self._bm[0]                                   # rows present in the staging copy
+        self.bitmap = done
+        mlo, mhi = self.shards[self.rank]
+        remote = [(a, b) for a, b in ((0, mlo), (mhi, self.V)) if b > a]
+        marks = []                                           # profiling: (label, event) on the side / main streams
+
+        def stamp(stream, label):
+            if profile is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream)
+                marks.append((label, ev))
+
         with torch.cuda.device(dev):
+            stamp(main, "start")
             self.hdl.barrier(channel=0)                       # every rank's views are in its symmetric buffer
             start = torch.cuda.Event()
             start.record(main)
+            stamp(main, "barrier")
             self.side.wait_event(start)
             arrived = []
             with torch.cuda.stream(self.side):
                 if order:
-                    self.bitmap.zero_()
-                    _lib.check(lib.cnrma_mark_rows(C.byref(grid), C.byref(box), C.c_void_p(P.data_ptr()), 12, self.V,
-                                                   float(stride), self.H, self.W, C.c_void_p(self.bitmap.data_ptr()),
-                                                   F._stream(dev)), "cnrma_mark_rows")
-                for q in order:
-                    qlo, qhi = self.shards[q]
-                    _lib.check(lib.cnrma_pull_rows(C.c_void_p(self.bitmap[qlo].data_ptr()), qhi - qlo, self.H, self.W,
-                                                   self.row_bytes, C.c_void_p(self.peers[q].data_ptr()), self.view_bytes,
-                                                   C.c_void_p(self.staging[qlo].data_ptr()), self.view_bytes,
-                                                   int(pull_ctas), F._stream(dev)), "cnrma_pull_rows")
+                    self._bm[: len(xparts) + 1].zero_()
+                    self._work.zero_()
+                    box = _lib.make_box(lo, dim)              # the rows every part needs from the remote views
+                    for a, b in remote:
+                        _lib.check(lib.cnrma_mark_rows(C.byref(grid), C.byref(box), C.c_void_p(P[a].data_ptr()), 12,
+                                                       b - a, float(stride), self.H, self.W,
+                                                       C.c_void_p(self._bm[1, a].data_ptr()), len(xparts),
+                                                       self.V * self.words, F._stream(dev)), "cnrma_mark_rows")
+                    stamp(self.side, "marks")
+                for k in range(len(xparts) if order else 0):
+                    _lib.check(lib.cnrma_pull_rows(C.c_void_p(self._bm[k + 1].data_ptr()), C.c_void_p(done.data_ptr()),
+                                                   self.V, self.H, self.W, self.row_bytes, self._owner_ptrs,
+                                                   C.c_void_p(self.staging.data_ptr()), self.view_bytes, pull_arg,
+                                                   C.c_void_p(self._work[k].data_ptr()), mhi % self.V, F._stream(dev)),
+                               "cnrma_pull_rows")
+                    ev = torch.cuda.Event()
+                    ev.record(self.side)
+                    arrived.append(ev)
+                    stamp(self.side, f"pull{k}")
+                if not order:
                     ev = torch.cuda.Event()
                     ev.record(self.side)
                     arrived.append(ev)
                 self.hdl.barrier(channel=1)                   # every rank is done reading its peers' buffers
                 released = torch.cuda.Event()
                 released.record(self.side)
-            bx, by, bz = dim
             buf = _lib.empty((1, bx, by, bz, self.C), dtype=torch.float32, device=dev)
             count = _lib.empty((1, 1, bx, by, bz), dtype=torch.int32, device=dev)
             valid = _lib.empty((1, 1, bx, by, bz), dtype=torch.bool, device=dev)
-            volume = buf.permute(0, 4, 1, 2, 3)
-
-            def launch(vlo, vhi, flags, reserve):
-                desc = self._descriptor(vlo, vhi)
+            desc = self._descriptor(0, self.V)
+            flags = _lib.AGG_MEAN if mean else 0
+            reserve = (int(pull_ctas) if pull_ctas else lib.cnrma_pull_default_ctas()) if len(xparts) > 1 else 0
+            plane = by * bz
+            for k, (x0, x1) in enumerate(xparts):
+                main.wait_event(arrived[k])
+                box = _lib.make_box((lo[0] + x0, lo[1], lo[2]), (x1 - x0, by, bz))
                 _lib.check(lib.cnrma_aggregate_views_box(
-                    C.byref(grid), C.byref(box), C.byref(desc), C.c_void_p(P[vlo].data_ptr()), 12, float(stride), flags,
-                    C.c_void_p(buf.data_ptr()), self.C, 1, C.c_void_p(count.data_ptr()), C.c_void_p(valid.data_ptr()),
-                    reserve, F._stream(dev)), "cnrma_aggregate_views_box")
-
-            fin = _lib.AGG_MEAN if mean else 0
-            if not overlap or not order:
-                for ev in arrived:
-                    main.wait_event(ev)
-                launch(0, self.V, fin, 0)
-            else:
-                reserve = int(pull_ctas) if pull_ctas else lib.cnrma_pull_default_ctas()
-                chunks = [(mlo, mhi, None)] if mhi > mlo else []
-                chunks += [(self.shards[q][0], self.shards[q][1], ev) for q, ev in zip(order, arrived)]
-                for k, (vlo, vhi, ev) in enumerate(chunks):
-                    if ev is not None:
-                        main.wait_event(ev)
-                    last = k == len(chunks) - 1
-                    launch(vlo, vhi, (_lib.AGG_ACCUMULATE if k > 0 else 0) | (fin if last else 0), 0 if last else reserve)
+                    C.byref(grid), C.byref(box), C.byref(desc), C.c_void_p(P.data_ptr()), 12, float(stride), flags,
+                    C.c_void_p(buf.data_ptr() + x0 * plane * self.C * 4), self.C, 1,
+                    C.c_void_p(count.data_ptr() + x0 * plane * 4), C.c_void_p(valid.data_ptr() + x0 * plane),
+                    reserve if k + 1 < len(xparts) else 0, F._stream(dev)), "cnrma_aggregate_views_box")
+                stamp(main, f"gather{k}")
             main.wait_event(released)                         # the next call may overwrite local_features()
-        return lo, dim, volume, count, valid
+            stamp(main, "end")
+        if profile is not None:
+            torch.cuda.synchronize(dev)
+            t0 = marks[0][1]
+            profile.update({label: t0.elapsed_time(ev) for label, ev in marks[1:]})
+        return lo, dim, buf.permute(0, 4, 1, 2, 3), count, valid

@@ -13,7 +13,9 @@ PyTorch is used for device memory, streams and the 4x4 LAPACK inverse the refere
 (rm.py:100); every other step runs in the CUDA library.  There is no CPU or eager fallback: tensors must
 live on a CUDA device and the library must be built.
 """
+import collections
 import ctypes as C
+import threading
 import types
 
 import torch
@@ -498,7 +500,31 @@ def _march(fs, b, P_scaled_b, tsdf_b, grid, voxel_dim, voxel_size, grids, mode, 
     return m
 
 
-_pinned_results = {}
+# Host-side state of the path.  All of it is either per thread (the pinned staging slot of the M read-back) or a
+# guarded hint (how many rows recent calls with the same shapes kept), so the functions of this module may be called
+# from several Python threads, each on its own stream -- the same contract as the C ABI underneath.
+_tls = threading.local()
+_state_lock = threading.Lock()
+_fill_counters = {"calls": 0, "speculative": 0, "misses": 0}
+_phase_hook = None
+
+
+def set_phase_hook(fn):
+    """Observer for profiling: fn(label) is called right after the kernels of a phase have been queued on the current
+    stream ("march" inside rma_points / rma_points_selected).  bench.py records CUDA events there; None removes it."""
+    global _phase_hook
+    _phase_hook = fn
+
+
+def fill_stats(reset=False):
+    """Counters of the speculative fill (see _march_and_fill): calls, launches made before M was known, and misses
+    (the row count exceeded the guess and the fill ran a second time)."""
+    with _state_lock:
+        out = dict(_fill_counters)
+        if reset:
+            for k in _fill_counters:
+                _fill_counters[k] = 0
+    return out
 
 
 def _read_result(m):
@@ -506,11 +532,14 @@ def _read_result(m):
     that waits only for the march / scan kernels (event recorded by _march), through a pinned staging buffer, so
     a fill kernel queued speculatively behind the march does not delay it."""
     dev = m.result.device
-    slot = _pinned_results.get(dev)
+    slots = getattr(_tls, "pinned", None)
+    if slots is None:
+        slots = _tls.pinned = {}
+    slot = slots.get(dev)
     if slot is None:
         slot = (torch.empty(C.sizeof(_lib.RmaResult), dtype=torch.uint8, pin_memory=True), torch.cuda.Event(),
                 torch.cuda.Stream(device=dev))
-        _pinned_results[dev] = slot
+        slots[dev] = slot
     host, event, side = slot
     side.wait_event(m.done)
     with torch.cuda.stream(side):
@@ -543,27 +572,49 @@ def _fill(fs, b, m, grid, rows_host, normalize, mean_tensor=None, desc=None, cap
     return rows
 
 
-# rows kept by the previous call with the same shapes: lets the fill kernel be queued before M has been read back
+# rows kept by recent calls with the same shapes: lets the fill kernel be queued before M has been read back
 _rows_hint = {}
 
 
+def _hint_rows(key):
+    """Capacity guess for `key`: the largest row count of its last eight calls plus 6 % headroom, or None."""
+    with _state_lock:
+        seen = _rows_hint.get(key)
+        if not seen:
+            return None
+        n = max(seen)
+    return n + n // 16 + 1024
+
+
+def _note_rows(key, n):
+    with _state_lock:
+        _rows_hint.setdefault(key, collections.deque(maxlen=8)).append(int(n))
+
+
 def _march_and_fill(fs, b, m, grid, normalize, mean_hook, key, desc=None):
-    """march result -> rows.  If an earlier call with the same shapes tells how many rows to expect, the fill is
-    launched speculatively into a buffer with 6 % headroom and the read-back of M (the path's one host sync)
-    overlaps with it; otherwise (first call, view-sharded mean, or the rare overflow) M is read first."""
+    """march result -> rows.  If earlier calls with the same shapes tell how many rows to expect, the fill is
+    launched speculatively into a buffer sized for the largest of them (+ 6 %) and the read-back of M (the path's one
+    host sync) overlaps with it; otherwise (first call, view-sharded mean, or a scene that keeps more rows than any
+    recent one) M is read first.  fill_stats() counts how often each happens."""
     device = fs.device
     desc = desc if desc is not None else fs.descriptor(b)
-    hint = _rows_hint.get(key)
+    hint = _hint_rows(key)
     rows = None
     if hint and mean_hook is None:
         rows = _fill(fs, b, m, grid, -1, normalize, None, desc, capacity=hint)
     res = _read_result(m)
     n = int(res.rows)
-    if rows is None or n > rows.shape[0]:
+    missed = rows is not None and n > rows.shape[0]
+    mean_t = None
+    if rows is None or missed:
         mean_t = mean_hook(res.weight_sum, res.rows, device) if (mean_hook and normalize) else None
         rows = _fill(fs, b, m, grid, n, normalize, mean_t, desc)
-    _rows_hint[key] = n + n // 16 + 1024
-    return rows[:n], res
+    _note_rows(key, n)
+    with _state_lock:
+        _fill_counters["calls"] += 1
+        _fill_counters["speculative"] += 1 if hint and mean_hook is None else 0
+        _fill_counters["misses"] += 1 if missed else 0
+    return rows[:n], res, mean_t
 
 
 def _check_mode(mode, threshold, depth_points):
@@ -603,9 +654,10 @@ def rma_points(projections, features, tsdf, voxel_dim, voxel_size, origin, strid
             # view-sharded callers replace the local mean weight by the all-reduced one (distributed.py)
             key = (device.index, b, fs.V, fs.C, fs.H, fs.W, tuple(int(v) for v in voxel_dim), int(grids), mode,
                    threshold, depth_points, bool(normalize))
-            rows, res = _march_and_fill(fs, b, m, grid, normalize, mean_hook, key)
+            if _phase_hook is not None:
+                _phase_hook("march")
+            rows, res, mean_t = _march_and_fill(fs, b, m, grid, normalize, mean_hook, key)
             if with_grad:
-                mean_t = mean_hook(res.weight_sum, res.rows, device) if (mean_hook and normalize) else None
                 inputs, stacked = _autograd_inputs(features, view_list)
                 state = dict(shape=(fs.V, fs.B, fs.C, fs.H, fs.W), device=device, grid=grid, march=m, b=b,
                              normalize=bool(normalize), mean=mean_t, stacked=stacked,
@@ -755,6 +807,25 @@ def _to_mask_dev(mask, n, device):
     return m.contiguous()
 
 
+class _SelectRowsBackward(torch.autograd.Function):
+    """Attaches the gradient of the ordered row selection to its result: kept row j came from row idx[j] of `points`,
+    `coord + offset` has gradient one (rm.py:362-402 are differentiable in the reference: the detection loss reaches the
+    2D features through the selected points)."""
+
+    @staticmethod
+    def forward(ctx, out, mask_dev, points):
+        ctx.save_for_backward(mask_dev)
+        ctx.shape = tuple(points.shape)
+        return out.view_as(out)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (mask_dev,) = ctx.saved_tensors
+        grad = torch.zeros(ctx.shape, dtype=grad_out.dtype, device=grad_out.device)
+        grad.masked_scatter_(mask_dev.unsqueeze(1).expand(ctx.shape), grad_out.contiguous())   # row order preserved
+        return None, None, grad
+
+
 def switch_pointcloud(points, offsets, max_points=None, masks=None, rng=None):
     """The tensor part of RayMarching.switch_pointcloud (rm.py:339-407; augmentation and boxes stay with the caller):
     per batch element `coord + offset`, then the rows kept by sample_points' mask, in order.
@@ -782,25 +853,60 @@ def switch_pointcloud(points, offsets, max_points=None, masks=None, rng=None):
                 prefix, _kept = _mask_prefix(mask_dev)
                 off3 = (C.c_float * 3)(*off)
                 src = pts if pts.stride(1) == 1 else pts.contiguous()
+                src = src.detach()
                 _lib.check(lib.cnrma_select_rows(C.c_void_p(src.data_ptr()), src.stride(0), cols, n,
                                                  C.c_void_p(mask_dev.data_ptr()), C.c_void_p(prefix.data_ptr()), off3,
                                                  C.c_void_p(out.data_ptr()), cols, n_sel, _stream(device)),
                            "cnrma_select_rows")
+        if torch.is_grad_enabled() and pts.requires_grad:
+            out = _SelectRowsBackward.apply(out, mask_dev, pts)
         coords.append(out[:, 0:3])
         feats.append(out[:, 3:])
     return coords, feats
 
 
+def _selected_without_sync(lib, fs, m, grid, desc, cap, max_points, seed, off, cols, device):
+    """Sampler (row count from the march's result block on the device), prefix sum and selected fill for at most `cap`
+    rows, queued without reading M: returns the [max_points, cols] buffer whose first min(M, max_points) rows are valid
+    provided M <= cap."""
+    mask = _lib.empty(cap, dtype=torch.bool, device=device)
+    nbytes = C.c_size_t(0)
+    _lib.check(lib.cnrma_sample_workspace_bytes(C.byref(nbytes)), "cnrma_sample_workspace_bytes")
+    ws = _lib.empty(nbytes.value, dtype=torch.uint8, device=device)
+    _lib.check(lib.cnrma_sample_mask_for_result(C.c_void_p(m.result.data_ptr()), cap, max_points,
+                                                seed & 0xFFFFFFFFFFFFFFFF, C.c_void_p(ws.data_ptr()), nbytes.value,
+                                                C.c_void_p(mask.data_ptr()), _stream(device)), "cnrma_sample_mask_for_result")
+    prefix, _kept = _mask_prefix(mask)
+    out = _lib.empty((max_points, cols), dtype=torch.float32, device=device)
+    off3 = (C.c_float * 3)(*off)
+    _lib.check(lib.cnrma_rma_fill_selected(
+        C.byref(grid), C.c_void_p(m.pinv.data_ptr()), C.byref(desc), m.grids, m.t_one, m.mode, m.threshold,
+        m.depth_points, C.c_void_p(m.workspace.data_ptr()), C.c_void_p(m.result.data_ptr()), 1, None,
+        C.c_void_p(mask.data_ptr()), C.c_void_p(prefix.data_ptr()), cap, off3, C.c_void_p(out.data_ptr()), cols, max_points,
+        _stream(device)), "cnrma_rma_fill_selected")
+    return out
+
+
 def rma_points_selected(projections, features, tsdf, voxel_dim, voxel_size, origin, stride, offsets, max_points=None,
-                        masks=None, rng=None, grids=300, mode="neus", threshold=None, depth_points=None):
+                        masks=None, rng=None, grids=300, mode="neus", threshold=None, depth_points=None,
+                        device_seed=None):
     """aggregate_2d_features_ray_marching (rm.py:260-307) fused with switch_pointcloud (rm.py:339-407): the march
     runs as usual, M is read back, the keep mask is drawn (or taken from `masks`: per batch element a mask or a
     callable `n -> mask`), and the fill kernel produces ONLY
     the kept rows, offset already added -- the un-sampled point cloud (M x (3+C) floats) is never written.
 
+    `device_seed` (with `max_points`): the mask is drawn on the device like sample_points_device, from the row count
+    the march leaves IN DEVICE MEMORY -- sampler, prefix sum and fill are queued right behind the march and M is read
+    back afterwards, so the host never stalls between the kernels (buffers are sized from recent calls with the same
+    shapes; the first call, or a scene that keeps more rows than any recent one, takes the path above).
+
+    Inference only: raises when a feature map requires grad (train through rma_points + switch_pointcloud, whose
+    results carry the backward kernels).
     Returns (coords list of [Nsel,3], features list of [Nsel,C]) like switch_pointcloud."""
     _check_mode(mode, threshold, depth_points)
     lib = _lib.load()
+    if _needs_grad([features] if isinstance(features, torch.Tensor) else _as_view_list(features)):
+        raise CnrmaError("rma_points_selected has no backward: use rma_points + switch_pointcloud when training")
     fs = _FeatureStack(features, need_vector_layout=False)
     device = fs.device
     if not isinstance(projections, torch.Tensor):
@@ -813,9 +919,31 @@ def rma_points_selected(projections, features, tsdf, voxel_dim, voxel_size, orig
             m = _march(fs, b, P_scaled[:, b], tsdf[b, 0], grid, voxel_dim, voxel_size, grids, mode, threshold,
                        depth_points)
             desc = fs.descriptor(b)
-            n = int(_read_result(m).rows)
-            mask = masks[b] if masks is not None else (sample_points(n, max_points, rng) if max_points is not None
-                                                       else None)
+            if _phase_hook is not None:
+                _phase_hook("march")
+            cols = fs.C + 3
+            key = ("selected", device.index, b, fs.V, fs.C, fs.H, fs.W, tuple(int(v) for v in voxel_dim), int(grids), mode,
+                   threshold, depth_points)
+            if device_seed is not None and max_points is not None and masks is None:
+                cap = _hint_rows(key)
+                if cap:
+                    out = _selected_without_sync(lib, fs, m, grid, desc, cap, int(max_points), int(device_seed) + b,
+                                                 _origin3(offsets[b]), cols, device)
+                    n = int(_read_result(m).rows)             # everything is queued: the host waits here only
+                    _note_rows(key, n)
+                    if n <= cap:
+                        out = out[: min(n, int(max_points))]
+                        coords.append(out[:, 0:3])
+                        feats.append(out[:, 3:])
+                        continue
+                else:
+                    n = int(_read_result(m).rows)
+                    _note_rows(key, n)
+                mask = sample_points_device(n, max_points, int(device_seed) + b, device)
+            else:
+                n = int(_read_result(m).rows)
+                mask = masks[b] if masks is not None else (sample_points(n, max_points, rng) if max_points is not None
+                                                           else None)
             if callable(mask):                      # drawn once M is known, e.g. lambda n: sample_points_device(n, ...)
                 mask = mask(n)
             if mask is None:
@@ -823,7 +951,6 @@ def rma_points_selected(projections, features, tsdf, voxel_dim, voxel_size, orig
             else:
                 n_sel = _mask_count(mask)
                 mask_dev = _to_mask_dev(mask, n, device)
-            cols = fs.C + 3
             out = _lib.empty((n_sel, cols), dtype=torch.float32, device=device)
             if n_sel > 0:
                 prefix, _kept = _mask_prefix(mask_dev)
@@ -831,7 +958,7 @@ def rma_points_selected(projections, features, tsdf, voxel_dim, voxel_size, orig
                 _lib.check(lib.cnrma_rma_fill_selected(
                     C.byref(grid), C.c_void_p(m.pinv.data_ptr()), C.byref(desc), m.grids, m.t_one, m.mode, m.threshold,
                     m.depth_points, C.c_void_p(m.workspace.data_ptr()), C.c_void_p(m.result.data_ptr()), 1, None,
-                    C.c_void_p(mask_dev.data_ptr()), C.c_void_p(prefix.data_ptr()), off3, C.c_void_p(out.data_ptr()),
+                    C.c_void_p(mask_dev.data_ptr()), C.c_void_p(prefix.data_ptr()), n, off3, C.c_void_p(out.data_ptr()),
                     cols, n_sel, _stream(device)), "cnrma_rma_fill_selected")
             coords.append(out[:, 0:3])
             feats.append(out[:, 3:])

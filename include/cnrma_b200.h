@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CNRMA_ABI_VERSION 1
+#define CNRMA_ABI_VERSION 2 /* 2: box / exchange entry points, mask_rows of cnrma_rma_fill_selected, cnrma_sample_mask_for_result */
 
 typedef enum cnrma_status {
     CNRMA_OK = 0,
@@ -134,15 +134,31 @@ int cnrma_aggregate_views_box(const cnrma_grid *grid, const cnrma_box *box, cons
  *   cnrma_mark_rows  sets bit (pixel % 32) of bitmap[view * words + pixel / 32], words = ceil(H*W / 32), for every
  *                    (view, pixel) some voxel of the box gathers (same projection arithmetic as the gather kernels,
  *                    so the set is exact).  The caller zeroes `bitmap` first; bits are only ever set.
- *   cnrma_pull_rows  copies the marked rows of `views` channels-last maps from `src` (view v at src + v*src_view_stride
- *                    bytes; a PEER-MAPPED pointer in the multi-GPU use: the reads cross NVLink) to the same offsets of
- *                    `dst` (local staging, dst + v*dst_view_stride), as TMA bulk copies global -> shared -> global in a
- *                    two-stage pipeline per warp.  row_bytes = C * sizeof(element), a multiple of 16, <= 8192.
- *                    ctas = 0 picks the default grid (cnrma_pull_default_ctas). */
+ *                    parts > 1 (<= 16, <= dim[0]): the box is cut into `parts` x-ranges at dim[0]*k/parts and range k
+ *                    marks its own bitmap at bitmap + k*part_stride (uint32 units) -- one launch for a box that is
+ *                    served part by part.
+ *   cnrma_pull_rows  copies the marked rows of `views` channels-last maps from their owners (src_view_ptrs_host[v]: HOST
+ *                    array of DEVICE pointers, PEER-MAPPED in the multi-GPU use: the reads cross NVLink) to the same
+ *                    offsets of `dst` (local staging, view v at dst + v*dst_view_stride), as TMA bulk copies global ->
+ *                    shared -> global in a two-stage pipeline per warp.  row_bytes = C * sizeof(element), a multiple
+ *                    of 16, <= 8192; up to 512 views per call.
+ *                    `work` (may be NULL): a zeroed device counter; warps then claim bitmap words one at a time, which
+ *                    balances sparse bitmaps (without it the words are dealt out round-robin).
+ *                    `first_view`: the walk over the views starts there and wraps around -- ranks that pull from the
+ *                    same owners start at different ones, so that no owner's NVLink egress serves every reader at once.
+ *                    `done` (same shape as bitmap, may be NULL): rows whose bit is set there are already in dst and
+ *                    are skipped; the rows this launch pulls are added to it -- lets a box be served part by part
+ *                    (the gather of one part runs while the next part's rows arrive) without pulling a row twice.
+ *                    ctas = 0 picks the default grid (cnrma_pull_default_ctas); OR CNRMA_PULL_LSU into it to move the
+ *                    rows with 16-byte loads / stores through registers instead of bulk copies -- the better path
+ *                    when the puller shares the SMs with the gather kernel, whose own bulk copies fill the TMA queues. */
+#define CNRMA_PULL_LSU 0x10000
 int cnrma_mark_rows(const cnrma_grid *grid, const cnrma_box *box, const float *projections, int64_t proj_view_stride,
-                    int views, float stride, int height, int width, uint32_t *bitmap, void *stream);
-int cnrma_pull_rows(const uint32_t *bitmap, int views, int height, int width, int row_bytes, const void *src,
-                    int64_t src_view_stride, void *dst, int64_t dst_view_stride, int ctas, void *stream);
+                    int views, float stride, int height, int width, uint32_t *bitmap, int parts, int64_t part_stride,
+                    void *stream);
+int cnrma_pull_rows(const uint32_t *bitmap, uint32_t *done, int views, int height, int width, int row_bytes,
+                    const void *const *src_view_ptrs_host, void *dst, int64_t dst_view_stride, int ctas, uint32_t *work,
+                    int first_view, void *stream);
 int cnrma_pull_default_ctas(void);
 
 /* OPT-IN extra, not a replacement of any reference function: Stage A with bilinear instead of nearest sampling
@@ -284,15 +300,22 @@ int cnrma_select_rows(const float *rows, int64_t row_stride, int cols, int64_t n
 int cnrma_sample_workspace_bytes(size_t *bytes);
 int cnrma_sample_mask(int64_t rows, int64_t keep, uint64_t seed, void *workspace, size_t workspace_bytes, uint8_t *mask,
                       void *stream);
+/* The same draw with the row count taken from the march's result block IN DEVICE MEMORY (result->rows, clamped to
+ * `capacity`, the length of `mask`), so that the hand-off can be queued behind the march without reading M back first:
+ * mask[i] = 1 for exactly min(keep, rows) of the first `rows` entries, 0 for every other i < capacity.  For equal
+ * (rows, keep, seed) the mask equals cnrma_sample_mask's. */
+int cnrma_sample_mask_for_result(const cnrma_rma_result *result, int64_t capacity, int64_t keep, uint64_t seed,
+                                 void *workspace, size_t workspace_bytes, uint8_t *mask, void *stream);
 
 /* cnrma_rma_fill fused with the hand-off: only the kept rows are produced (at out row prefix[row], offset added),
  * i.e. aggregate_2d_features_ray_marching + switch_pointcloud in one pass.  mask / prefix index the M rows of the
- * march in their (view, v, u, step) order. */
+ * march in their (view, v, u, step) order and hold `mask_rows` entries: rows beyond them are dropped (0: they cover
+ * every row), which lets the launch be queued with buffers sized from a guess of M before M has been read back. */
 int cnrma_rma_fill_selected(const cnrma_grid *grid, const float *pinv, const cnrma_features *features, int grids,
                             float t_one, int mode, float threshold, int depth_points, const void *workspace,
                             const cnrma_rma_result *result, int normalize, const float *mean, const uint8_t *mask,
-                            const int32_t *prefix, const float *offset_host, float *rows, int64_t row_stride,
-                            int64_t capacity, void *stream);
+                            const int32_t *prefix, int64_t mask_rows, const float *offset_host, float *rows,
+                            int64_t row_stride, int64_t capacity, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * GT TSDF fusion (offline data preparation): TSDFFusion.integrate, data_prepare/scannet/tsdf.py:402-451 (same code in

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/cnrma_b200.h but not exported"
     assert sorted(cn.EXPORTS) == declared, "ctypes signature table and header disagree"
-    assert lib.cnrma_abi_version() == 1
+    assert lib.cnrma_abi_version() == 2
     assert lib.cnrma_status_string(-2).decode().startswith("feature maps")
 
 

@@ -32,7 +32,7 @@ def test_c_client_builds_and_fails_cleanly_without_gpu(tmp_path):
     exe = _build(tmp_path)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "abi version 1" in out.stdout
+    assert "abi version 2" in out.stdout
     if not torch.cuda.is_available():
         assert "no usable device" in out.stdout
 

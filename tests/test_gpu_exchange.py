@@ -56,8 +56,31 @@ def _mark(cn, sc, p, lo, dim, H, W):
     grid = _lib.make_grid(sc.voxel_dim, sc.voxel_size, sc.origin)
     box = _lib.make_box(lo, dim)
     _lib.check(lib.cnrma_mark_rows(C.byref(grid), C.byref(box), C.c_void_p(p.data_ptr()), 12, sc.views, float(sc.stride),
-                                   H, W, C.c_void_p(bitmap.data_ptr()), None), "cnrma_mark_rows")
+                                   H, W, C.c_void_p(bitmap.data_ptr()), 1, 0, None), "cnrma_mark_rows")
     return bitmap
+
+
+def test_mark_rows_in_parts_equals_separate_marks(cn):
+    from cnrma_b200 import _lib, distributed as D
+    lib = cn.load()
+    sc, f, p = _scene(cn, 16)
+    H, W = sc.height, sc.width
+    words = (H * W + 31) // 32
+    grid = _lib.make_grid(sc.voxel_dim, sc.voxel_size, sc.origin)
+    lo, dim = (3, 1, 2), (11, 17, 5)
+    for parts in (2, 3, 11):
+        bm = torch.zeros((parts, sc.views, words), dtype=torch.int32, device="cuda")
+        box = _lib.make_box(lo, dim)
+        _lib.check(lib.cnrma_mark_rows(C.byref(grid), C.byref(box), C.c_void_p(p.data_ptr()), 12, sc.views, float(sc.stride),
+                                       H, W, C.c_void_p(bm.data_ptr()), parts, sc.views * words, None), "cnrma_mark_rows")
+        for k, (x0, x1) in enumerate(D.x_chunks(dim[0], parts)):
+            one = _mark(cn, sc, p, (lo[0] + x0, lo[1], lo[2]), (x1 - x0, dim[1], dim[2]), H, W)
+            assert torch.equal(bm[k], one), (parts, k)
+
+
+def _ptrs(t):
+    """HOST array of the device pointers of t[0], t[1], ... (cnrma_pull_rows' src_view_ptrs_host)."""
+    return (C.c_void_p * t.shape[0])(*[t[v].data_ptr() for v in range(t.shape[0])])
 
 
 def _bits(bitmap, pixels):
@@ -97,14 +120,41 @@ def test_pull_rows_copies_exactly_the_marked_rows(cn, channels, dtype):
         bitmap = torch.from_numpy(np.packbits(bits, axis=1, bitorder="little").view(np.int32).copy()).cuda()
         dst = torch.full_like(src, -7.0)
         row_bytes = channels * src.element_size()
-        for ctas in (0, 1, 3):
+        for ctas in (0, 1, 3, 0x10000, 0x10002):          # CNRMA_PULL_LSU: the load/store path
             dst.fill_(-7.0)
-            _lib.check(lib.cnrma_pull_rows(C.c_void_p(bitmap.data_ptr()), V, H, W, row_bytes, C.c_void_p(src.data_ptr()),
-                                           H * W * row_bytes, C.c_void_p(dst.data_ptr()), H * W * row_bytes, ctas, None),
-                       "cnrma_pull_rows")
+            work = torch.zeros(1, dtype=torch.int32, device="cuda")
+            _lib.check(lib.cnrma_pull_rows(C.c_void_p(bitmap.data_ptr()), None, V, H, W, row_bytes, _ptrs(src),
+                                           C.c_void_p(dst.data_ptr()), H * W * row_bytes, ctas,
+                                           C.c_void_p(work.data_ptr()) if ctas != 3 else None, (ctas & 0xFFFF) % V, None), "cnrma_pull_rows")
             torch.cuda.synchronize()
             want = torch.where(mask.view(V, H, W, 1), src, torch.full_like(src, -7.0))
             assert torch.equal(dst, want), (channels, density, ctas)
+
+
+def test_pull_rows_skips_and_records_rows_already_present(cn):
+    from cnrma_b200 import _lib
+    lib = cn.load()
+    V, H, W, channels = 2, 8, 16, 64
+    g = torch.Generator(device="cuda").manual_seed(6)
+    src = torch.randn((V, H, W, channels), device="cuda", generator=g)
+    a = torch.rand((V, H * W), device="cuda", generator=g) < 0.4
+    b = torch.rand((V, H * W), device="cuda", generator=g) < 0.4
+    pack = lambda m: torch.from_numpy(np.packbits(m.cpu().numpy().astype(np.uint8), axis=1, bitorder="little").view(np.int32).copy()).cuda()
+    done = torch.zeros((V, H * W // 32), dtype=torch.int32, device="cuda")
+    dst = torch.full_like(src, -7.0)
+    rb = channels * 4
+    call = lambda bm: _lib.check(lib.cnrma_pull_rows(C.c_void_p(bm.data_ptr()), C.c_void_p(done.data_ptr()), V, H, W, rb,
+                                                     _ptrs(src), C.c_void_p(dst.data_ptr()), H * W * rb, 0, None, 1, None),
+                                 "cnrma_pull_rows")
+    call(pack(a))
+    assert torch.equal(done, pack(a))
+    dst[a.view(V, H, W)] = -3.0                         # if the second call pulled these again they would be restored
+    call(pack(b))
+    torch.cuda.synchronize()
+    assert torch.equal(done, pack(a | b))
+    want = torch.where((b & ~a).view(V, H, W, 1), src, torch.full_like(src, -7.0))
+    want[a.view(V, H, W)] = -3.0
+    assert torch.equal(dst, want)
 
 
 @pytest.mark.parametrize("channels,world", [(16, 2), (256, 4), (256, 8), (32, 3)])
@@ -128,9 +178,9 @@ def test_exchange_on_one_gpu_with_simulated_ranks(cn, channels, world):
             qlo, qhi = D.view_shard(sc.views, q, world)
             if q == rank or qhi == qlo:
                 continue
-            _lib.check(lib.cnrma_pull_rows(C.c_void_p(bitmap[qlo].data_ptr()), qhi - qlo, H, W, row_bytes,
-                                           C.c_void_p(rows[qlo].data_ptr()), H * W * row_bytes,
-                                           C.c_void_p(staging[qlo].data_ptr()), H * W * row_bytes, 0, None), "cnrma_pull_rows")
+            _lib.check(lib.cnrma_pull_rows(C.c_void_p(bitmap[qlo].data_ptr()), None, qhi - qlo, H, W, row_bytes,
+                                           _ptrs(rows[qlo:qhi]), C.c_void_p(staging[qlo].data_ptr()), H * W * row_bytes, 0,
+                                           None, 0, None), "cnrma_pull_rows")
         staging[mlo:mhi] = rows[mlo:mhi]
         fv = [staging[v].permute(2, 0, 1).unsqueeze(0) for v in range(sc.views)]
         bv, bc, bm = cn.aggregate_views(p, fv, *args, mean=True, box=(lo, dim))
@@ -147,11 +197,11 @@ def test_box_and_exchange_argument_errors(cn):
         cn.aggregate_views(p, f, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride, box=((0, 0, 0), (sc.voxel_dim[0] + 1, 1, 1)))
     bitmap = torch.zeros(64, dtype=torch.int32, device="cuda")
     buf = torch.zeros(4096, dtype=torch.float32, device="cuda")
-    assert lib.cnrma_pull_rows(C.c_void_p(bitmap.data_ptr()), 1, 4, 4, 24, C.c_void_p(buf.data_ptr()), 384,
-                               C.c_void_p(buf.data_ptr()), 384, 0, None) == -2          # row_bytes not a multiple of 16
-    assert lib.cnrma_pull_rows(None, 1, 4, 4, 32, C.c_void_p(buf.data_ptr()), 512, C.c_void_p(buf.data_ptr()), 512, 0,
-                               None) == -1
+    one = (C.c_void_p * 1)(buf.data_ptr())
+    assert lib.cnrma_pull_rows(C.c_void_p(bitmap.data_ptr()), None, 1, 4, 4, 24, one, C.c_void_p(buf.data_ptr()), 384, 0,
+                               None, 0, None) == -2                                     # row_bytes not a multiple of 16
+    assert lib.cnrma_pull_rows(None, None, 1, 4, 4, 32, one, C.c_void_p(buf.data_ptr()), 512, 0, None, 0, None) == -1
     grid = _lib.make_grid(sc.voxel_dim, sc.voxel_size, sc.origin)
     bad = _lib.make_box((0, 0, 0), (sc.voxel_dim[0], sc.voxel_dim[1], sc.voxel_dim[2] + 1))
     assert lib.cnrma_mark_rows(C.byref(grid), C.byref(bad), C.c_void_p(p.data_ptr()), 12, 1, 4.0, 4, 4,
-                               C.c_void_p(bitmap.data_ptr()), None) == -1
+                               C.c_void_p(bitmap.data_ptr()), 1, 0, None) == -1

@@ -187,10 +187,8 @@ def _worker_exchange(rank, world, port, ret):
                 sl = tuple(slice(l, l + d) for l, d in zip(blo, bdim))
                 good = torch.equal(cnt[0, 0], c1[0, 0][sl]) and torch.equal(valid[0, 0], m1[0, 0][sl])
                 ref = v1[0][(slice(None),) + sl]
-                if overlap:
-                    good = good and float((vol[0] - ref).abs().max()) / scale <= 1e-5
-                else:                                                      # view-order sums: the single-GPU bits
-                    good = good and torch.equal(vol[0].contiguous().view(torch.int32), ref.contiguous().view(torch.int32))
+                # all views in view order, whatever the pipelining: the single-GPU bits
+                good = good and torch.equal(vol[0].contiguous().view(torch.int32), ref.contiguous().view(torch.int32))
                 ok, why = ok and good, why or ("" if good else f"C={channels} overlap={overlap}")
         ok = ok and ex.pulled_bytes() >= 0
     ret[f"ok{rank}"] = ok
@@ -203,7 +201,7 @@ def _worker_exchange(rank, world, port, ret):
 @pytest.mark.parametrize("world", WORLDS)
 def test_voxel_sharded_feature_exchange(world):
     """ViewExchange: views in by rank, boxes of the volume out by rank; feature rows pulled over NVLink by the TMA
-    puller.  Without overlap the result is bit-identical to one GPU."""
+    puller.  The result is bit-identical to one GPU, with or without the part-by-part overlap."""
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     port = 29900 + (os.getpid() % 1000) + world

@@ -515,22 +515,26 @@ def test_many_views_short_rows_batches(cn, views, channels, dtype):
 
 @pytest.mark.parametrize("channels", [8, 256])
 def test_speculative_fill_with_wrong_row_hint(cn, channels):
-    """rma_points launches the fill before M is read back, into a buffer sized from the previous call with the same
-    shapes (functional._rows_hint).  A hint that is too small makes the kernel drop the rows beyond the capacity and
-    the host refill; a hint that is too large just leaves slack.  Both must give the rows of a first call -- for the
-    packed (short rows) and the TMA-store (long rows) fill kernels."""
+    """rma_points launches the fill before M is read back, into a buffer sized from recent calls with the same
+    shapes (functional._rows_hint: the largest of the last eight row counts + 6 %).  A guess that is too small makes
+    the kernel drop the rows beyond the capacity and the host refill; one that is too large just leaves slack.  Both
+    must give the rows of a first call -- for the packed (short rows) and the TMA-store (long rows) fill kernels."""
+    import collections
     import cnrma_b200.functional as F
     sc = cn.synthetic.make_scene("small", seed=4, channels=channels)
     p, f, t = _scene_tensors(sc)
     args = (sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
     F._rows_hint.clear()
     first = cn.rma_points(p, f, t, *args, grids=sc.grids, threshold=0.05)[0].clone()     # no hint: M read first
-    assert len(F._rows_hint) == 1 and first.shape[0] > 2000
+    assert len(F._rows_hint) == 1 and first.shape[0] > 4000
     key = next(iter(F._rows_hint))
-    for hint in (1, 777, first.shape[0] - 1, first.shape[0], 3 * first.shape[0]):
-        F._rows_hint[key] = hint
+    F.fill_stats(reset=True)
+    for seen in (1, 777, first.shape[0], 3 * first.shape[0]):      # capacities 1025, 1849 (too small), M + 6 %, 3 M + 6 %
+        F._rows_hint[key] = collections.deque([seen], maxlen=8)
         again = cn.rma_points(p, f, t, *args, grids=sc.grids, threshold=0.05)[0]
-        assert again.shape == first.shape and torch.equal(again, first), hint
+        assert again.shape == first.shape and torch.equal(again, first), seen
+    st = F.fill_stats()
+    assert st == {"calls": 4, "speculative": 4, "misses": 2}, st
 
 
 def test_march_prepass_fused_equals_unfused(cn, scene, monkeypatch):
