@@ -3,7 +3,8 @@ projects/mvsdetection/models/ray_marching.py behind the reference's own function
 
 Import name: `cnrma_b200` (see the alias package at the repository root; '-' is not valid in a module name).
 """
-from ._lib import CnrmaError, build, load, LIB_PATH, EXPORTS  # noqa: F401
+from ._lib import CnrmaError, build, load, reload_tuning, LIB_PATH, EXPORTS  # noqa: F401
+from . import _lib  # noqa: F401
 from .functional import (aggregate_views, aggregate_views_bilinear, backproject, dense_rma, finalize_views, get_ray_parameter,  # noqa: F401
                          invert_projections, project_views, rma_points_selected, sample_points, sample_points_device,
                          switch_pointcloud, ray_projection, rma_dense_weights, rma_points, scale_projections)

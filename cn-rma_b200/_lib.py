@@ -103,6 +103,7 @@ _SIGNATURES = {
     "cnrma_status_string": (C.c_char_p, [C.c_int]),
     "cnrma_last_cuda_error": (C.c_int, []),
     "cnrma_check_device": (C.c_int, []),
+    "cnrma_reload_tuning": (None, []),
     "cnrma_project_views": (C.c_int, [C.POINTER(Grid), C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cnrma_aggregate_views": (C.c_int, [C.POINTER(Grid), C.POINTER(Features), C.c_void_p, C.c_int64, C.c_float,
@@ -185,6 +186,11 @@ def load():
                 raise CnrmaError("libcnrma_b200.so ABI version mismatch")
             _lib = lib
     return _lib
+
+
+def reload_tuning():
+    """Re-reads the CNRMA_* tuning knobs from the environment (the library reads them once; tests flip them)."""
+    load().cnrma_reload_tuning()
 
 
 def check(status, what=""):

@@ -9,6 +9,31 @@ namespace cnrma {
 
 static thread_local int g_last_cuda_error = 0;
 
+static Tuning read_tuning() {
+    Tuning t;
+    auto num = [](const char *name) { const char *e = std::getenv(name); return e ? std::atoi(e) : 0; };
+    if (const char *e = std::getenv("CNRMA_AGG_KERNEL")) t.agg_kernel = (e[0] == 'l') ? 1 : 0;
+    t.agg_slab = num("CNRMA_AGG_SLAB");
+    t.agg_tile = num("CNRMA_AGG_TILE");
+    t.agg_chunk_bytes = num("CNRMA_AGG_CHUNK_BYTES");
+    t.agg_warp_buffer = num("CNRMA_AGG_WARP_BUFFER");
+    t.agg_list_views = num("CNRMA_AGG_LIST_VIEWS");
+    if (const char *e = std::getenv("CNRMA_AGG_BWD_KERNEL")) t.agg_bwd_kernel = (e[0] == 'l') ? 1 : 0;
+    t.bilinear_simple = std::getenv("CNRMA_BILINEAR_SIMPLE") != nullptr;
+    t.march_unfused = std::getenv("CNRMA_MARCH_UNFUSED_PREPASS") != nullptr;
+    if (const char *e = std::getenv("CNRMA_FILL_KERNEL")) t.fill_kernel = (e[0] == 'p') ? 1 : 0;
+    t.fill_stage_half = num("CNRMA_FILL_STAGE_HALF");
+    if (const char *e = std::getenv("CNRMA_FILL_SELECT_KERNEL")) t.fill_select_scalar = (e[0] == 's');
+    return t;
+}
+
+static Tuning &tuning_slot() {
+    static Tuning t = read_tuning();   // thread-safe one-time initialisation
+    return t;
+}
+
+const Tuning &tuning() { return tuning_slot(); }
+
 static int fail_cuda(cudaError_t e) {
     g_last_cuda_error = (int)e;
     return CNRMA_ERR_CUDA;
@@ -19,6 +44,10 @@ static bool grid_ok(const cnrma_grid *g) {
     if (!(g->voxel_size > 0.0f)) return false;
     return (int64_t)g->nx * g->ny * g->nz < (int64_t)1 << 31;
 }
+
+// The Stage A sweep decodes voxel coordinates with fast_divmod (cnrma_common.cuh), exact for quotients below 2^22:
+// the largest quotient is an (x, y) column index, so planes of 4 M columns and more are refused instead of mis-decoded.
+static bool sweep_ok(int nx, int ny) { return (int64_t)nx * ny < ((int64_t)1 << 22); }
 
 static int features_ok(const cnrma_features *f, bool need_channels_last, bool allow_empty = false) {
     if (f && allow_empty && f->views == 0 && f->channels > 0 && (f->dtype == CNRMA_F32 || f->dtype == CNRMA_BF16))
@@ -73,6 +102,8 @@ int cnrma_last_cuda_error(void) { return g_last_cuda_error; }
 
 int cnrma_check_device(void) { return device_ok(); }
 
+void cnrma_reload_tuning(void) { tuning_slot() = read_tuning(); }
+
 int cnrma_project_views(const cnrma_grid *grid, const float *projections, int64_t proj_view_stride, int views,
                         float stride, int height, int width, int32_t *px, int32_t *py, uint8_t *valid, void *stream) {
     if (!grid_ok(grid) || !projections || views <= 0 || height <= 0 || width <= 0 || !(stride > 0.0f))
@@ -99,6 +130,7 @@ static int aggregate_views_impl(const cnrma_grid *grid, const cnrma_box *box, co
                                 uint8_t *valid, int reserve_ctas, void *stream) {
     if (!grid_ok(grid) || !features || !volume || !count || !(stride > 0.0f)) return CNRMA_ERR_ARG;
     if (box && !box_ok(grid, box)) return CNRMA_ERR_ARG;
+    if (!(box ? sweep_ok(box->dim[0], box->dim[1]) : sweep_ok(grid->nx, grid->ny))) return CNRMA_ERR_UNSUPPORTED;
     if (!projections && features->views > 0) return CNRMA_ERR_ARG;
     if (flags & ~(CNRMA_AGG_ACCUMULATE | CNRMA_AGG_MEAN | CNRMA_AGG_COUNT_F32)) return CNRMA_ERR_ARG;
     const int fs = features_ok(features, true, (flags & CNRMA_AGG_ACCUMULATE) != 0);
@@ -106,8 +138,7 @@ static int aggregate_views_impl(const cnrma_grid *grid, const cnrma_box *box, co
     const int d = device_ok();
     if (d != CNRMA_OK) return d;
     // Tuning knob (DESIGN.md "K_A"): cap on the bytes of a feature row gathered per channel pass (<= 1024).
-    int max_chunk_vecs = 0;
-    if (const char *env = std::getenv("CNRMA_AGG_CHUNK_BYTES")) max_chunk_vecs = std::atoi(env);
+    const int max_chunk_vecs = tuning().agg_chunk_bytes;
     const GridDev g = box ? to_dev_box(*grid, *box) : to_dev(*grid);
     // Views go out in batches that accumulate into the volume in view order (the fp32 chain of the reference's
     // `self.volume + volume` loop is unchanged).  Short rows with many views are split into batches the list kernel
@@ -116,8 +147,7 @@ static int aggregate_views_impl(const cnrma_grid *grid, const cnrma_box *box, co
     int batch = kMaxViewsPerLaunch;
     const int row_bytes = features->channels * (features->dtype == CNRMA_BF16 ? 2 : 4);
     if (row_bytes < 512 && features->views > kListViewsMax) {
-        int per = kListViewsBatch;
-        if (const char *env = std::getenv("CNRMA_AGG_LIST_VIEWS")) per = std::atoi(env);   // tuning aid
+        const int per = tuning().agg_list_views > 0 ? tuning().agg_list_views : kListViewsBatch;   // tuning aid
         if (per >= 1 && per <= kListViewsMax) {
             const int nbatch = (features->views + per - 1) / per;
             batch = (features->views + nbatch - 1) / nbatch;
@@ -196,11 +226,11 @@ int cnrma_aggregate_views_bilinear(const cnrma_grid *grid, const cnrma_features 
     if (flags & ~CNRMA_AGG_MEAN) return CNRMA_ERR_ARG;
     const int fs = features_ok(features, true);
     if (fs != CNRMA_OK) return fs;
-    if (features->views > kMaxViewsPerLaunch) return CNRMA_ERR_UNSUPPORTED;
+    if (features->views > kMaxViewsPerLaunch || !sweep_ok(grid->nx, grid->ny)) return CNRMA_ERR_UNSUPPORTED;
     const int d = device_ok();
     if (d != CNRMA_OK) return d;
     cudaError_t e;
-    if (std::getenv("CNRMA_BILINEAR_SIMPLE") != nullptr)   // the first, simple kernel (kept as a second opinion for the tests)
+    if (tuning().bilinear_simple)   // the first, simple kernel (kept as a second opinion for the tests)
         e = run_aggregate_bilinear(to_dev(*grid), *features, projections, proj_view_stride, stride, flags, volume, count,
                                    valid, static_cast<cudaStream_t>(stream));
     else
@@ -217,7 +247,8 @@ int cnrma_aggregate_views_routed(const cnrma_grid *grid, const cnrma_features *f
     if (n_owners < 1 || n_owners > kMaxOwners || slab_voxels < 1) return CNRMA_ERR_ARG;
     const int fs = features_ok(features, true);
     if (fs != CNRMA_OK) return fs;
-    if (features->views < 1 || features->views > kMaxViewsPerLaunch) return CNRMA_ERR_UNSUPPORTED;
+    if (features->views < 1 || features->views > kMaxViewsPerLaunch || !sweep_ok(grid->nx, grid->ny))
+        return CNRMA_ERR_UNSUPPORTED;
     const int64_t nvox = (int64_t)grid->nx * grid->ny * grid->nz;
     if ((int64_t)n_owners * slab_voxels < nvox || row_floats < features->channels + 1 || row_floats % 4 != 0)
         return CNRMA_ERR_ARG;
@@ -413,7 +444,7 @@ int cnrma_aggregate_views_backward(const cnrma_grid *grid, const cnrma_features 
     if (flags & ~CNRMA_AGG_MEAN) return CNRMA_ERR_ARG;
     const int fs = features_ok(grad_features, true);
     if (fs != CNRMA_OK) return fs;
-    if (grad_features->dtype != CNRMA_F32) return CNRMA_ERR_UNSUPPORTED;
+    if (grad_features->dtype != CNRMA_F32 || !sweep_ok(grid->nx, grid->ny)) return CNRMA_ERR_UNSUPPORTED;
     const int d = device_ok();
     if (d != CNRMA_OK) return d;
     const cudaError_t e = run_aggregate_views_backward(to_dev(*grid), *grad_features, projections, proj_view_stride, stride,

@@ -272,7 +272,7 @@ cudaError_t run_aggregate_views_backward(const GridDev &g, const cnrma_features 
                                          int64_t vsv, int64_t vsc, const int32_t *count, cudaStream_t stream) {
     // short rows: list kernel with vector reductions (CNRMA_AGG_BWD_KERNEL=bulk|list overrides)
     bool use_list = gf.channels * 4 < 512;
-    if (const char *env = std::getenv("CNRMA_AGG_BWD_KERNEL")) use_list = (env[0] == 'l');
+    if (tuning().agg_bwd_kernel >= 0) use_list = tuning().agg_bwd_kernel == 1;   // CNRMA_AGG_BWD_KERNEL
     if (use_list) {
         const cudaError_t e = run_aggregate_views_backward_list(g, gf, proj, proj_stride, stride, flags, grad_volume, vsv, vsc,
                                                                 count, stream);

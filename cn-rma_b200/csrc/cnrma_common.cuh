@@ -21,6 +21,24 @@ constexpr int kAggThreads = 256;            // 8 warps per CTA
 constexpr int kMaxViewsPerLaunch = 512;     // per-view device pointers travel in kernel params (4 KB of the 32 KB CUDA >= 12.1 allows)
 constexpr int kRayThreads = 256;            // rays per CTA in the march / fill kernels
 
+// Tuning / test knobs (environment variables, DESIGN.md "Tuning / test knobs"), read ONCE per process -- the launch path
+// never calls getenv -- and again only on cnrma_reload_tuning() (the tests flip knobs between calls).
+struct Tuning {
+    int agg_kernel = -1;        // CNRMA_AGG_KERNEL: -1 automatic, 0 tma, 1 list
+    int agg_slab = 0;           // CNRMA_AGG_SLAB: slab thickness of the Stage A sweep, 0 automatic
+    int agg_tile = 0;           // CNRMA_AGG_TILE: (x, y) tile edge inside a slab, 0 none
+    int agg_chunk_bytes = 0;    // CNRMA_AGG_CHUNK_BYTES
+    int agg_warp_buffer = 0;    // CNRMA_AGG_WARP_BUFFER
+    int agg_list_views = 0;     // CNRMA_AGG_LIST_VIEWS
+    int agg_bwd_kernel = -1;    // CNRMA_AGG_BWD_KERNEL: -1 automatic, 0 bulk, 1 list
+    int bilinear_simple = 0;    // CNRMA_BILINEAR_SIMPLE
+    int march_unfused = 0;      // CNRMA_MARCH_UNFUSED_PREPASS
+    int fill_kernel = -1;       // CNRMA_FILL_KERNEL: -1 automatic, 0 tma, 1 packed
+    int fill_stage_half = 0;    // CNRMA_FILL_STAGE_HALF
+    int fill_select_scalar = 0; // CNRMA_FILL_SELECT_KERNEL=scalar
+};
+const Tuning &tuning();
+
 struct GridDev {
     int nx, ny, nz;
     float vs;
@@ -208,6 +226,10 @@ __device__ __forceinline__ void fast_divmod(int n, int d, float inv_d, int &q, i
 struct SweepOrder {
     int ny, T, Tlast, nfull, full;   // full = nx*ny*T voxels per full slab, nfull full slabs, then one of Tlast slices
     float inv_full, inv_T, inv_Tlast, inv_ny;
+    // optional (x, y) tiling inside a slab (tile > 0, both extents multiples of it): tiles of tile x tile columns are
+    // swept one after the other, x-major, each column over the slab's z -- a more compact window in x and y
+    int tile, tiles_y;
+    float inv_tile, inv_tile2, inv_tiles_y;
 };
 
 inline SweepOrder make_sweep(int nx, int ny, int nz, int T) {
@@ -222,13 +244,26 @@ inline SweepOrder make_sweep(int nx, int ny, int nz, int T) {
     s.inv_T = 1.0f / (float)s.T;
     s.inv_Tlast = 1.0f / (float)s.Tlast;
     s.inv_ny = 1.0f / (float)ny;
+    s.tile = 0;
+    s.tiles_y = 1;
+    s.inv_tile = s.inv_tile2 = s.inv_tiles_y = 1.0f;
+    {   // tuning aid (CNRMA_AGG_TILE)
+        const int t = tuning().agg_tile;
+        if (t > 1 && nx % t == 0 && ny % t == 0) {
+            s.tile = t;
+            s.tiles_y = ny / t;
+            s.inv_tile = 1.0f / (float)t;
+            s.inv_tile2 = 1.0f / (float)(t * t);
+            s.inv_tiles_y = 1.0f / (float)s.tiles_y;
+        }
+    }
     return s;
 }
 
 // Slab thickness: the window holds about L2_window / (visible views x row bytes) voxels; make it as deep in z as it is
 // long in x (it always spans y): T = sqrt(window_voxels / ny).  A quarter of the views see a voxel in the scenes at hand.
 inline int sweep_thickness(int ny, int nz, int views, int row_bytes) {
-    if (const char *env = std::getenv("CNRMA_AGG_SLAB")) return std::atoi(env);   // tuning aid
+    if (tuning().agg_slab > 0) return tuning().agg_slab;   // tuning aid (CNRMA_AGG_SLAB)
     const double per_voxel = 0.25 * (views > 0 ? views : 1) * (row_bytes > 0 ? row_bytes : 1);
     const double window_voxels = 64.0 * 1024 * 1024 / per_voxel;
     int T = (int)(std::sqrt(window_voxels / (ny > 0 ? ny : 1)) + 0.5);
@@ -241,6 +276,15 @@ __device__ __forceinline__ void sweep_voxel(const SweepOrder &s, int it, int &vx
     const bool last = slab >= s.nfull;
     fast_divmod(rem, last ? s.Tlast : s.T, last ? s.inv_Tlast : s.inv_T, xy, zi);
     vz = slab * s.T + zi;
+    if (s.tile > 0) {
+        int t, in_tile, tx, ty, lx, ly;
+        fast_divmod(xy, s.tile * s.tile, s.inv_tile2, t, in_tile);
+        fast_divmod(t, s.tiles_y, s.inv_tiles_y, tx, ty);
+        fast_divmod(in_tile, s.tile, s.inv_tile, lx, ly);
+        vx = tx * s.tile + lx;
+        vy = ty * s.tile + ly;
+        return;
+    }
     fast_divmod(xy, s.ny, s.inv_ny, vx, vy);
 }
 

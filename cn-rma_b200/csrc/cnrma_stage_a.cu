@@ -313,7 +313,7 @@ static cudaError_t run_aggregate(const AggParams &p_in, int dtype, int max_chunk
     p.chunk_bytes = plan_chunk_bytes(p.C * esz, max_chunk_bytes);
     const int chunks = (p.C * esz) / p.chunk_bytes;
     int warp_buffer = p.bilinear ? 2 * kWarpBufferBytes : kWarpBufferBytes;   // bilinear: 2 CTAs per SM, 12 KB per warp
-    if (const char *env = std::getenv("CNRMA_AGG_WARP_BUFFER")) warp_buffer = std::atoi(env);   // tuning aid
+    if (tuning().agg_warp_buffer > 0) warp_buffer = tuning().agg_warp_buffer;   // tuning aid (CNRMA_AGG_WARP_BUFFER)
     p.rows_cap = warp_buffer / p.chunk_bytes;
     if (p.rows_cap < 1) p.rows_cap = 1;
     if (p.rows_cap > 32) p.rows_cap = 32;
@@ -355,7 +355,7 @@ cudaError_t run_aggregate_views(const GridDev &g, const cnrma_features &f, int v
     const int row_bytes = f.channels * ((f.dtype == CNRMA_BF16) ? 2 : 4);
     // (beyond ~96 views the per-voxel lists no longer fit 32 voxels per warp and the list kernel loses its edge)
     bool use_list = ((row_bytes < 512 && nv <= kListViewsMax) || nv == 0) && !(flags & kAggBilinearInternal);
-    if (const char *env = std::getenv("CNRMA_AGG_KERNEL")) use_list = (env[0] == 'l') && !(flags & kAggBilinearInternal);   // tuning aid: "list" / "tma"
+    if (tuning().agg_kernel >= 0) use_list = (tuning().agg_kernel == 1) && !(flags & kAggBilinearInternal);   // CNRMA_AGG_KERNEL
     if (use_list && list_kernel_supports(nv, f.height, f.width))
         return run_aggregate_list(g, f, v0, nv, proj, proj_stride, stride, flags, volume, vsv, vsc, count, valid, stream, route,
                                   reserve_ctas);

@@ -819,7 +819,7 @@ cudaError_t run_march(const GridDev &g, const float *pinv, int V, int H, int W, 
     cudaError_t err = cudaSuccess;
     const int nvox = g.nx * g.ny * g.nz;
     const size_t slab_bytes = 2 * (size_t)g.ny * g.nz;
-    const bool slab = mode == CNRMA_MARCH_NEUS && slab_bytes <= 96 * 1024 && std::getenv("CNRMA_MARCH_UNFUSED_PREPASS") == nullptr;
+    const bool slab = mode == CNRMA_MARCH_NEUS && slab_bytes <= 96 * 1024 && !tuning().march_unfused;
     if (!slab) {
         err = cudaMemsetAsync(result, 0, sizeof(cnrma_rma_result), stream);
         if (err != cudaSuccess) return err;
@@ -1093,11 +1093,14 @@ static cudaError_t launch_fill(FillParams &p, int dtype, const void *const *view
         static thread_local int attr_dev[24] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
                                                 -1, -1, -1, -1, -1, -1, -1, -1};   // dynamic-smem opt-in, once per device
         int dev = 0;
-        cudaGetDevice(&dev);
+        cudaError_t attr_err = cudaGetDevice(&dev);
+        if (attr_err != cudaSuccess) return attr_err;
         const int nj = (p.C + 31) / 32;
         auto go = [&](auto kernel, int slot) {
             if (attr_dev[slot] != dev) {
-                cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kRayThreads / kWarp) * kStageBytes));
+                attr_err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)((kRayThreads / kWarp) * kStageBytes));
+                if (attr_err != cudaSuccess) return;   // reported after the dispatch below; nothing is launched
                 attr_dev[slot] = dev;
             }
             kernel<<<blocks, kRayThreads, smem, stream>>>(p);
@@ -1105,7 +1108,7 @@ static cudaError_t launch_fill(FillParams &p, int dtype, const void *const *view
         // hand-off selection fused in: the packed kernel's SELECT form (CNRMA_FILL_SELECT_KERNEL=scalar: the plain kernel)
         bool select_packed = !SCATTER && p.sel_mask != nullptr && p.row_stride == cols && p.C <= 32 * kFillRegs &&
                              cols * 4 <= kHalfStageBytes - 16 && reinterpret_cast<uintptr_t>(p.rows) % 4 == 0;
-        if (const char *env = std::getenv("CNRMA_FILL_SELECT_KERNEL")) select_packed = select_packed && env[0] != 's';
+        if (tuning().fill_select_scalar) select_packed = false;   // CNRMA_FILL_SELECT_KERNEL=scalar
         if (select_packed) {
             p.stage_half = (cols * 4 <= 2048 - 16) ? 2048 : kHalfStageBytes;
             smem = (size_t)(kRayThreads / kWarp) * 2 * p.stage_half;
@@ -1123,12 +1126,12 @@ static cudaError_t launch_fill(FillParams &p, int dtype, const void *const *view
         } else if (tma) {
             // short rows: per-ray work dominates -> the packed kernel (CNRMA_FILL_KERNEL=tma|packed overrides)
             bool packed = cols * 4 <= kPackedRowBytesMax;
-            if (const char *env = std::getenv("CNRMA_FILL_KERNEL")) packed = (env[0] == 'p') && cols * 4 <= kHalfStageBytes - 16;
+            if (tuning().fill_kernel >= 0) packed = (tuning().fill_kernel == 1) && cols * 4 <= kHalfStageBytes - 16;   // CNRMA_FILL_KERNEL
             if (packed) {
                 // small staging halves for short rows: more resident CTAs (the kernel is latency-bound there)
                 // (measured: 2 KB halves beat 4 KB ones on 140-, 268- and 524-byte rows alike; 1 KB ones lose)
                 p.stage_half = (cols * 4 <= 2048 - 16) ? 2048 : kHalfStageBytes;
-                if (const char *env = std::getenv("CNRMA_FILL_STAGE_HALF")) p.stage_half = std::atoi(env);
+                if (tuning().fill_stage_half > 0) p.stage_half = tuning().fill_stage_half;   // CNRMA_FILL_STAGE_HALF
                 smem = (size_t)(kRayThreads / kWarp) * 2 * p.stage_half;
                 if (dtype == CNRMA_BF16) {
                     if (nj <= 1) go(fill_rows_packed_kernel<__nv_bfloat16, 1, false>, 8);
@@ -1157,6 +1160,7 @@ static cudaError_t launch_fill(FillParams &p, int dtype, const void *const *view
         } else {
             fill_rows_kernel<float, SCATTER><<<blocks, kRayThreads, 0, stream>>>(p);
         }
+        if (attr_err != cudaSuccess) return attr_err;   // the shared-memory opt-in of a fill kernel failed
         const cudaError_t err = cudaGetLastError();
         if (err != cudaSuccess) return err;
     }

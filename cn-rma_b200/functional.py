@@ -406,11 +406,18 @@ def backproject(voxel_dim, voxel_size, origin, projection, features):
 # Stage B
 # ----------------------------------------------------------------------------------------------------
 
+_inverse_lock = threading.Lock()
+
+
 def invert_projections(projections_scaled):
     """rm.py:96-102: inverse of [P; 0 0 0 1] per view with the reference's own LAPACK call (torch.inverse, CPU,
-    fp32) on the host, so the ray parameters are bit-identical to the CPU reference.  The batched call runs the
-    same per-matrix getrf/getri as the reference's one-matrix calls (bit-identical, checked in the tests); it is
-    issued single-threaded because OpenMP fan-out over fifty 4x4 matrices costs milliseconds.
+    fp32) on the host, so the ray parameters are bit-identical to the reference RUN ON THE CPU (a reference run on a GPU
+    inverts with cuSOLVER / MAGMA, whose last bits differ: parity of Stage B is defined against the CPU run, as
+    SURVEY.md section 8 does).  The batched call runs the same per-matrix getrf/getri as the reference's one-matrix
+    calls (bit-identical, checked in the tests); it is issued single-threaded because OpenMP fan-out over fifty 4x4
+    matrices costs milliseconds -- the thread count is a process-wide torch setting, so the toggle is serialised.
+    Pass host tensors when the cameras are known on the host (they come from the data loader): a CUDA tensor is
+    copied back first, which synchronises the stream.
     projections_scaled [V,3,4] (any device) -> [V,4,4] CPU fp32 (pinned when CUDA is available)."""
     P = projections_scaled.detach().to("cpu", torch.float32)
     V = P.shape[0]
@@ -418,6 +425,7 @@ def invert_projections(projections_scaled):
     p4[:, :3, :] = P
     p4[:, 3, 3] = 1.0
     out = torch.empty((V, 4, 4), dtype=torch.float32, pin_memory=torch.cuda.is_available())
+    _inverse_lock.acquire()
     threads = torch.get_num_threads()
     torch.set_num_threads(1)
     try:
@@ -433,6 +441,7 @@ def invert_projections(projections_scaled):
                     out[v].fill_(float("nan"))
     finally:
         torch.set_num_threads(threads)
+        _inverse_lock.release()
     return out
 
 

@@ -88,6 +88,9 @@ const char *cnrma_status_string(int status);
 int cnrma_last_cuda_error(void);
 /* CNRMA_OK when the current CUDA device can run the kernels (compute capability 10.x). */
 int cnrma_check_device(void);
+/* The tuning / test knobs (CNRMA_* environment variables) are read once, at the first call that needs one;
+ * this re-reads them (for tests that flip a knob between calls; not for use while other threads are launching). */
+void cnrma_reload_tuning(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Stage A -- dense back-projection (voxel driven)

@@ -19,6 +19,33 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(autouse=True)
+def _tuning_knobs_follow_the_environment(monkeypatch):
+    """The library reads its CNRMA_* knobs once per process.  Tests flip them with monkeypatch.setenv / os.environ: this
+    wraps setenv / delenv so that the library re-reads them right away, and re-reads once more after the test (when
+    monkeypatch has restored the environment)."""
+    import cnrma_b200
+    loaded = os.path.exists(cnrma_b200.LIB_PATH)
+    if loaded:
+        real_set, real_del = monkeypatch.setenv, monkeypatch.delenv
+
+        def setenv(name, value, *a, **kw):
+            real_set(name, value, *a, **kw)
+            if name.startswith("CNRMA_"):
+                cnrma_b200.reload_tuning()
+
+        def delenv(name, *a, **kw):
+            real_del(name, *a, **kw)
+            if name.startswith("CNRMA_"):
+                cnrma_b200.reload_tuning()
+
+        monkeypatch.setenv, monkeypatch.delenv = setenv, delenv
+    yield
+    if loaded:
+        monkeypatch.undo()
+        cnrma_b200.reload_tuning()
+
+
 def golden_names():
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
 

@@ -151,3 +151,96 @@ def test_other_configs_run(cn, name):
                                   return_stats=True)
     assert pts.shape[0] == st["rows"] > 0
     assert bool(torch.isfinite(pts).all())
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Parity at size for the other BASELINE configurations: the CUDA path against the oracle on the configuration's own
+# grid, map size, channel count and dtype, over as many views as the oracle lifts in seconds.
+# ----------------------------------------------------------------------------------------------------------------
+
+def _sized_scene(cn, name, views, seed=2):
+    sc = cn.synthetic.make_scene(name, seed=seed, with_features=False)
+    stride = max(1, sc.views // views)
+    ids = list(range(0, sc.views, stride))[:views]          # spread over the camera ring
+    sc.projections = np.ascontiguousarray(sc.projections[ids])
+    dev = torch.device("cuda")
+    feats = cn.synthetic.device_features(sc, dev, channels_last=True)      # [views,1,C,H,W]
+    proj = torch.from_numpy(sc.projections).to(dev).unsqueeze(1)
+    tsdf = torch.from_numpy(sc.tsdf).to(dev)[None, None]
+    return sc, feats, proj, tsdf
+
+
+def _check_stage_a_against_oracle(cn, sc, feats, proj, f_host):
+    """indices / masks (every view), counts, un-averaged sums and means: bit-exact."""
+    args = (sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
+    px, py, valid = cn.project_views(proj, *args, sc.height, sc.width)
+    for v in range(sc.views):
+        opx, opy, ovalid = oracle.project(sc.voxel_dim, sc.voxel_size, sc.origin,
+                                          oracle.scale_projection(sc.projections[v], sc.stride), sc.height, sc.width)
+        gv = valid[v, 0].cpu().numpy()
+        assert np.array_equal(gv, ovalid), f"mask of view {v}"
+        assert np.array_equal(px[v, 0].cpu().numpy()[gv], opx[gv]) and np.array_equal(py[v, 0].cpu().numpy()[gv], opy[gv])
+    del px, py, valid
+    for mean in (False, True):
+        vol, cnt, ok = cn.aggregate_views(proj, feats, *args, mean=mean)
+        ovol, ocnt = oracle.aggregate_views(sc.projections, f_host, *args, mean=mean)
+        assert np.array_equal(cnt[0, 0].cpu().numpy(), ocnt)
+        assert np.array_equal(ok[0, 0].cpu().numpy(), ocnt > 0)
+        got = vol[0].contiguous().cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), ovol.view(np.uint32)), f"Stage A volume (mean={mean})"
+        del vol, cnt, ok, got, ovol
+    return ocnt
+
+
+def _check_stage_b_against_oracle(cn, sc, feats, proj, tsdf, f_host, views):
+    ref = oracle.aggregate_2d_features_ray_marching(sc.projections[:views], f_host[:views], sc.tsdf, sc.voxel_dim,
+                                                    sc.voxel_size, sc.origin, sc.stride, grids=sc.grids, normalize=False)
+    (rows,) = cn.rma_points(proj[:views], feats[:views], tsdf, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride,
+                            grids=sc.grids, threshold=0.05, normalize=False)
+    got = rows.cpu().numpy()
+    assert got.shape == ref.shape
+    assert np.array_equal(got[:, :3].view(np.uint32), ref[:, :3].view(np.uint32))
+    assert np.array_equal(got[:, 4:].view(np.uint32), ref[:, 4:].view(np.uint32))
+    assert_rel(got[:, 3], ref[:, 3], 1e-5, what="weights")
+
+
+@pytest.mark.parametrize("name", ["cfg3", "cfg4"])
+def test_config_sized_parity_fp32(cn, name):
+    """cfg 3 (ARKit-shaped: 256 ch @ 256x192 maps, 96x96x40) and cfg 4 (fine grid 160x160x64, 256 ch): 4 views through
+    Stage A, the first of them through Stage B, against the oracle."""
+    sc, feats, proj, tsdf = _sized_scene(cn, name, 4)
+    f_host = feats[:, 0].contiguous().cpu().numpy()
+    ocnt = _check_stage_a_against_oracle(cn, sc, feats, proj, f_host)
+    assert int(ocnt.max()) >= 2
+    _check_stage_b_against_oracle(cn, sc, feats, proj, tsdf, f_host, 1)
+
+
+def test_config_sized_parity_cfg5_bf16_many_views(cn):
+    """cfg 5 (long-ray stress): bf16 maps with 128 channels, the full 256x256x96 grid, N = 256 march steps, and 132 views
+    so that the list kernel runs three view batches that accumulate into the volume in view order.  Counts and sums
+    bit-exact against the oracle on the widened values (bf16 -> fp32 is exact), and within north_star's 2e-3 of the
+    oracle on the un-quantised fp32 maps."""
+    sc, feats32, proj, tsdf = _sized_scene(cn, "cfg5", 132)
+    assert sc.grids == 256 and sc.voxel_dim == (256, 256, 96) and sc.channels == 128
+    feats = feats32.to(torch.bfloat16)
+    args = (sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
+    f_wide = feats[:, 0].float().contiguous().cpu().numpy()
+    vol, cnt, ok = cn.aggregate_views(proj, feats, *args, mean=True)
+    ovol, ocnt = oracle.aggregate_views(sc.projections, f_wide, *args, mean=True)
+    assert int(ocnt.max()) > 63, "a voxel should be seen by more views than one list batch holds"
+    assert np.array_equal(cnt[0, 0].cpu().numpy(), ocnt)
+    got = vol[0].contiguous().cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), ovol.view(np.uint32)), "cfg 5 Stage A volume"
+    del ovol, f_wide
+    oexact, _ = oracle.aggregate_views(sc.projections, feats32[:, 0].contiguous().cpu().numpy(), *args, mean=True)
+    err = float(np.abs(got - oexact).max() / np.abs(oexact).max())
+    assert err <= 2e-3, f"bf16 features: {err:.2e}"
+    del oexact, got, vol
+    # masks of a few views, and Stage B (N = 256) on two views
+    px, py, valid = cn.project_views(proj[:3], *args, sc.height, sc.width)
+    for v in range(3):
+        _opx, _opy, ovalid = oracle.project(sc.voxel_dim, sc.voxel_size, sc.origin,
+                                            oracle.scale_projection(sc.projections[v], sc.stride), sc.height, sc.width)
+        assert np.array_equal(valid[v, 0].cpu().numpy(), ovalid)
+    del px, py, valid
+    _check_stage_b_against_oracle(cn, sc, feats, proj, tsdf, feats[:, 0].float().contiguous().cpu().numpy(), 2)

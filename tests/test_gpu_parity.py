@@ -456,10 +456,12 @@ def _check_bilinear(cn, sc, dtype):
     assert torch.equal(cnt, cnt_nearest)
     import os
     os.environ["CNRMA_BILINEAR_SIMPLE"] = "1"        # the first, straightforward kernel: same formula, same order
+    cn.reload_tuning()
     try:
         vol_simple, cnt_simple, _ = cn.aggregate_views_bilinear(p, f, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
     finally:
         del os.environ["CNRMA_BILINEAR_SIMPLE"]
+        cn.reload_tuning()
     assert torch.equal(cnt, cnt_simple) and torch.equal(vol, vol_simple)
     nx, ny, nz = sc.voxel_dim
     g = torch.stack(torch.meshgrid(torch.arange(nx), torch.arange(ny), torch.arange(nz), indexing="ij"), 0).reshape(3, -1)
@@ -503,10 +505,12 @@ def test_many_views_short_rows_batches(cn, views, channels, dtype):
             os.environ.pop("CNRMA_AGG_KERNEL", None)
         else:
             os.environ["CNRMA_AGG_KERNEL"] = kernel
+        cn.reload_tuning()
         try:
             vol, cnt, _ = cn.aggregate_views(p, f, sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride, mean=True)
         finally:
             os.environ.pop("CNRMA_AGG_KERNEL", None)
+            cn.reload_tuning()
         assert np.array_equal(cnt[0, 0].cpu().numpy(), ocnt), kernel
         assert np.array_equal(vol[0].cpu().numpy().view(np.uint32), ovol.view(np.uint32)), kernel
         results.append(vol)
@@ -579,3 +583,13 @@ def test_routed_stage_a_single_gpu_simulation(cn, channels, owners):
     assert not bool(torch.isnan(vol).any())
     scale = float(want_vol.abs().max())
     assert float((vol - want_vol[0]).abs().max()) <= 1e-5 * scale
+
+
+def test_planes_beyond_the_sweep_decoder_are_refused(cn):
+    """fast_divmod decodes (x, y) column indices exactly below 2^22 only: a wider plane gets CNRMA_ERR_UNSUPPORTED."""
+    f = torch.zeros((1, 1, 4, 2, 2), device="cuda").permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+    p = torch.eye(4, device="cuda")[:3].reshape(1, 1, 3, 4).contiguous()
+    with pytest.raises(cn.CnrmaError, match="unsupported"):
+        cn.aggregate_views(p, f, (4096, 1024, 1), 0.1, (0.0, 0.0, 0.0), 1.0)
+    vol, cnt, _ = cn.aggregate_views(p, f, (2048, 1024, 1), 0.1, (0.0, 0.0, 0.0), 1.0)     # just below: served
+    assert tuple(cnt.shape) == (1, 1, 2048, 1024, 1)

@@ -21,6 +21,44 @@ pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference tree
 SEEDS = int(os.environ.get("CNRMA_REFERENCE_SEEDS", "40"))
 
 
+def _assert_differences_are_banded(ref_rows, keep, places, wraw, thr, view):
+    """Walks the oracle's samples in flat (v, u, step) order -- the order of the reference's rows -- and pairs them with
+    the reference's rows by bit-identical position.  A sample only the oracle keeps, or only the reference keeps, must
+    have |w - thr| <= 1e-5 * thr; every reference row must be paired."""
+    band = np.abs(wraw - thr) <= 1e-5 * thr
+    ref_pos = np.ascontiguousarray(ref_rows[:, :3]).view(np.uint32)
+    pos = np.ascontiguousarray(places).view(np.uint32)
+    j = 0
+    only_oracle = only_ref = 0
+    for i in np.nonzero(keep | band)[0]:
+        match = j < ref_pos.shape[0] and np.array_equal(pos[i], ref_pos[j])
+        if keep[i] and match:
+            j += 1
+        elif keep[i]:
+            assert band[i], f"view {view}: sample {i} kept by the oracle only, weight {wraw[i]} outside the band of {thr}"
+            only_oracle += 1
+        elif match:                      # band[i] holds here: the reference keeps a banded sample the oracle drops
+            j += 1
+            only_ref += 1
+    assert j == ref_pos.shape[0], f"view {view}: {ref_pos.shape[0] - j} reference rows have no counterpart among the oracle's samples"
+    assert only_oracle + only_ref > 0
+
+
+def test_band_check_catches_differences_outside_the_band():
+    """The checker itself: a row dropped or added outside the threshold band must fail, inside it must pass."""
+    thr = 0.05
+    places = np.arange(30, dtype=np.float32).reshape(10, 3)
+    wraw = np.array([0.2, 0.01, 0.05 * (1 + 5e-6), 0.3, 0.05 * (1 - 5e-6), 0.0, 0.4, 0.02, 0.5, 0.6], np.float32)
+    keep = wraw >= thr
+    rows = lambda idx: np.concatenate([places[idx], wraw[idx, None]], 1)
+    # the reference drops banded sample 2 and keeps banded sample 4: fine
+    _assert_differences_are_banded(rows([0, 3, 4, 6, 8, 9]), keep, places, wraw, thr, 0)
+    with pytest.raises(AssertionError):          # the reference lacks un-banded sample 3
+        _assert_differences_are_banded(rows([0, 2, 6, 8, 9]), keep, places, wraw, thr, 0)
+    with pytest.raises(AssertionError):          # the reference has un-banded sample 1
+        _assert_differences_are_banded(rows([0, 1, 2, 3, 6, 8, 9]), keep, places, wraw, thr, 0)
+
+
 @pytest.mark.parametrize("seed", range(SEEDS))
 def test_oracle_equals_reference_on_random_scene(seed):
     rm = ref_shim.load_reference()
@@ -69,11 +107,11 @@ def test_oracle_equals_reference_on_random_scene(seed):
                 continue
             ref_rows = r[0].numpy()
             if ro is None or ro.shape != ref_rows.shape:
-                # kept sets may differ only for weights within 1e-5 of the threshold (band protocol)
-                dense_w, _keep = oracle.neus_dense(oracle.invert_projection(oracle.scale_projection(s["projs"][v], stride)), H, W, N,
-                                                   dim, vs, origin, s["tsdf"], thr)
-                band = np.abs(dense_w - thr) <= 1e-5 * thr
-                assert band.any(), f"view {v}: kept sets differ outside the threshold band"
+                # kept sets may differ only in samples whose weight is within 1e-5 of the threshold (band protocol):
+                # every row one side has and the other lacks is identified and its weight checked
+                _w, keep, places, wraw = oracle.neus_dense(oracle.invert_projection(oracle.scale_projection(s["projs"][v], stride)),
+                                                          H, W, N, dim, vs, origin, s["tsdf"], thr)
+                _assert_differences_are_banded(ref_rows, keep.ravel(), places.reshape(-1, 3), wraw.ravel(), thr, v)
                 continue
             assert np.array_equal(ro[:, :3].view(np.uint32), ref_rows[:, :3].view(np.uint32))
             assert np.array_equal(ro[:, 4:].view(np.uint32), ref_rows[:, 4:].view(np.uint32))
