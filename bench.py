@@ -753,8 +753,13 @@ def run_e2e(args, cn, scenes, dev, world, max_rows, handoff_rows=None):
         return pts.shape[0]
 
     steps = max(2, min(args.steps, 6))
+    # warm-up: three full steps, so that the caching allocator owns every block the pipeline cycles through (a result
+    # block stays busy until its download is done; a cudaMalloc in the timed region would synchronise the device)
     upload(0)
-    compute_and_download(0)
+    for k in range(3):
+        if k < 2:
+            upload(k + 1)
+        compute_and_download(k)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

@@ -159,6 +159,11 @@ _SIGNATURES = {
     "cnrma_sample_mask": (C.c_int, [C.c_int64, C.c_int64, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "cnrma_sample_mask_for_result": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p,
                                                C.c_void_p]),
+    "cnrma_quantize_workspace_bytes": (C.c_int, [C.c_int64, C.POINTER(C.c_size_t)]),
+    "cnrma_quantize_mark": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_size_t, C.c_void_p,
+                                      C.c_void_p]),
+    "cnrma_quantize_compact": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_float, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "cnrma_tsdf_integrate": (C.c_int, [C.POINTER(Grid), C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_void_p),
                                        C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_float,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

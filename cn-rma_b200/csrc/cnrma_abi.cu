@@ -15,6 +15,7 @@ static Tuning read_tuning() {
     if (const char *e = std::getenv("CNRMA_AGG_KERNEL")) t.agg_kernel = (e[0] == 'l') ? 1 : 0;
     t.agg_slab = num("CNRMA_AGG_SLAB");
     t.agg_tile = num("CNRMA_AGG_TILE");
+    if (const char *e = std::getenv("CNRMA_AGG_CULL")) t.agg_cull = std::atoi(e) != 0;
     t.agg_chunk_bytes = num("CNRMA_AGG_CHUNK_BYTES");
     t.agg_warp_buffer = num("CNRMA_AGG_WARP_BUFFER");
     t.agg_list_views = num("CNRMA_AGG_LIST_VIEWS");
@@ -499,6 +500,39 @@ int cnrma_sample_mask_for_result(const cnrma_rma_result *result, int64_t capacit
     static_assert(sizeof(long long) == sizeof(int64_t), "rows is read as long long");
     const cudaError_t e = run_sample_mask(capacity, keep, seed, workspace, mask, static_cast<cudaStream_t>(stream),
                                           reinterpret_cast<const long long *>(&result->rows));
+    return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
+}
+
+int cnrma_quantize_workspace_bytes(int64_t rows, size_t *bytes) {
+    if (!bytes || rows < 0) return CNRMA_ERR_ARG;
+    if (rows >= ((int64_t)1 << 30)) return CNRMA_ERR_UNSUPPORTED;
+    *bytes = quantize_workspace_bytes(rows);
+    return CNRMA_OK;
+}
+
+int cnrma_quantize_mark(const float *rows, int64_t row_stride, int64_t n_rows, float voxel_size, void *workspace,
+                        size_t workspace_bytes, uint8_t *keep, void *stream) {
+    if (!rows || !workspace || !keep || row_stride < 3 || n_rows < 0 || !(voxel_size > 0.0f)) return CNRMA_ERR_ARG;
+    if (n_rows >= ((int64_t)1 << 30)) return CNRMA_ERR_UNSUPPORTED;
+    if (workspace_bytes < quantize_workspace_bytes(n_rows)) return CNRMA_ERR_CAPACITY;
+    if (reinterpret_cast<uintptr_t>(workspace) % 8 != 0) return CNRMA_ERR_LAYOUT;
+    const int d = device_ok();
+    if (d != CNRMA_OK) return d;
+    const cudaError_t e = run_quantize_mark(rows, row_stride, n_rows, voxel_size, workspace, keep,
+                                            static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
+}
+
+int cnrma_quantize_compact(const float *rows, int64_t row_stride, int cols, int64_t n_rows, float voxel_size,
+                           const uint8_t *keep, const int32_t *prefix, float *out, int64_t out_stride, int32_t *cells,
+                           int64_t capacity, void *stream) {
+    if (!rows || !keep || !prefix || !out || cols < 3 || row_stride < cols || out_stride < cols || n_rows < 0 ||
+        capacity < 0 || !(voxel_size > 0.0f))
+        return CNRMA_ERR_ARG;
+    const int d = device_ok();
+    if (d != CNRMA_OK) return d;
+    const cudaError_t e = run_quantize_compact(rows, row_stride, cols, n_rows, voxel_size, keep, prefix, out, out_stride,
+                                               cells, capacity, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? CNRMA_OK : fail_cuda(e);
 }
 

@@ -279,3 +279,157 @@ cudaError_t run_sample_mask(int64_t n, int64_t k, unsigned long long seed, void 
 }
 
 }  // namespace cnrma
+
+// ---- quantisation of the hand-off (rm.py:330-332) ---------------------------------------------------------------
+// The reference hands `coords / voxel_size_fcaf3d` (0.01 m) to MinkowskiEngine 0.5.4 (`ME.utils.batch_sparse_collate`
+// then `ME.SparseTensor`; third-party, not vendored): the collate step stores the float coordinates into an int32 tensor
+// (truncation toward zero), and the sparse tensor keeps ONE row per occupied cell (its default quantisation mode picks
+// an arbitrary duplicate -- whichever thread wins on the GPU).  Here the deterministic member of that family: the FIRST
+// row of every cell in row order survives, survivors stay in row order.
+//   insert   open-addressing hash table keyed by the packed cell (3 x 21 bits); every row atomicMin's its index into its
+//            cell's slot
+//   keep     a row survives iff it is the minimum of its cell
+//   compact  survivors (whole rows + their int32 cells) written in order through the mask's prefix sum
+namespace cnrma {
+
+constexpr unsigned long long kQuantEmpty = ~0ull;
+constexpr int kQuantRange = 1 << 20;   // |cell index| below 2^20 on every axis (10 km at 0.01 m)
+
+__device__ __forceinline__ bool quant_cell(const float *__restrict__ row, float vs, int q[3]) {
+    bool ok = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float f = __fdiv_rn(__ldg(row + a), vs);     // coord / voxel_size: IEEE division (torch CPU, rm.py:331)
+        ok = ok && (f > -(float)kQuantRange) && (f < (float)kQuantRange);   // also false for NaN
+        q[a] = ok ? (int)f : 0;                            // float -> int32: truncation toward zero
+    }
+    return ok;
+}
+
+__device__ __forceinline__ unsigned long long quant_key(const int q[3]) {
+    return ((unsigned long long)(unsigned)(q[0] + kQuantRange) << 42) | ((unsigned long long)(unsigned)(q[1] + kQuantRange) << 21) |
+           (unsigned long long)(unsigned)(q[2] + kQuantRange);
+}
+
+__device__ __forceinline__ unsigned int quant_hash(unsigned long long k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return (unsigned int)k;
+}
+
+__global__ void __launch_bounds__(256) quantize_insert_kernel(const float *__restrict__ rows, int64_t stride, int64_t n,
+                                                              float vs, unsigned long long *keys, int *vals,
+                                                              unsigned int slot_mask, int *bad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int q[3];
+    if (!quant_cell(rows + i * stride, vs, q)) {
+        *bad = 1;
+        return;
+    }
+    const unsigned long long key = quant_key(q);
+    unsigned int h = quant_hash(key) & slot_mask;
+    for (;;) {
+        const unsigned long long prev = atomicCAS(keys + h, kQuantEmpty, key);
+        if (prev == kQuantEmpty || prev == key) {
+            atomicMin(vals + h, (int)i);
+            return;
+        }
+        h = (h + 1) & slot_mask;
+    }
+}
+
+__global__ void __launch_bounds__(256) quantize_keep_kernel(const float *__restrict__ rows, int64_t stride, int64_t n, float vs,
+                                                            const unsigned long long *__restrict__ keys,
+                                                            const int *__restrict__ vals, unsigned int slot_mask,
+                                                            uint8_t *__restrict__ keep) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int q[3];
+    if (!quant_cell(rows + i * stride, vs, q)) {
+        keep[i] = 0;
+        return;
+    }
+    const unsigned long long key = quant_key(q);
+    unsigned int h = quant_hash(key) & slot_mask;
+    while (keys[h] != key) h = (h + 1) & slot_mask;        // the key was inserted by the first pass
+    keep[i] = (uint8_t)(vals[h] == (int)i);
+}
+
+// one warp per 32 rows; surviving rows are copied whole (coalesced) and their cells written as int32
+__global__ void __launch_bounds__(kSelThreads) quantize_compact_kernel(const float *__restrict__ rows, int64_t stride, int cols,
+                                                                       int64_t n, float vs, const uint8_t *__restrict__ keep,
+                                                                       const int32_t *__restrict__ prefix,
+                                                                       float *__restrict__ out, int64_t out_stride,
+                                                                       int32_t *__restrict__ cells, int64_t capacity) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (kSelThreads / kWarp) + (threadIdx.x >> 5);
+    const int64_t r0 = warp * 32;
+    if (r0 >= n) return;
+    const int64_t mine = r0 + lane;
+    const bool k = mine < n && keep[mine];
+    const int dst_mine = k ? prefix[mine] : -1;
+    if (k && dst_mine < capacity && cells != nullptr) {
+        int q[3];
+        quant_cell(rows + mine * stride, vs, q);
+        cells[(int64_t)dst_mine * 3 + 0] = q[0];
+        cells[(int64_t)dst_mine * 3 + 1] = q[1];
+        cells[(int64_t)dst_mine * 3 + 2] = q[2];
+    }
+    const unsigned bits = __ballot_sync(0xffffffffu, k);
+    for (unsigned b = bits; b; b &= b - 1) {
+        const int j = __ffs(b) - 1;
+        const int64_t dst = __shfl_sync(0xffffffffu, dst_mine, j);
+        if (dst >= capacity) continue;
+        const float *src = rows + (r0 + j) * stride;
+        float *d = out + dst * out_stride;
+        for (int c = lane; c < cols; c += 32) __stcs(d + c, __ldg(src + c));
+    }
+}
+
+static unsigned int quant_slots(int64_t n) {
+    unsigned int s = 1024;
+    while ((int64_t)s < 2 * n) s <<= 1;
+    return s;
+}
+
+size_t quantize_workspace_bytes(int64_t n) {
+    const size_t slots = quant_slots(n);
+    return slots * 8 + slots * 4 + 256;
+}
+
+cudaError_t run_quantize_mark(const float *rows, int64_t stride, int64_t n, float vs, void *workspace, uint8_t *keep,
+                              cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const unsigned int slots = quant_slots(n);
+    unsigned char *base = static_cast<unsigned char *>(workspace);
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(base);
+    int *vals = reinterpret_cast<int *>(base + (size_t)slots * 8);
+    int *bad = reinterpret_cast<int *>(base + (size_t)slots * 12);
+    cudaError_t err = cudaMemsetAsync(keys, 0xFF, (size_t)slots * 8, stream);
+    if (err != cudaSuccess) return err;
+    err = cudaMemsetAsync(vals, 0x7F, (size_t)slots * 4, stream);   // 0x7F7F7F7F: larger than any row index
+    if (err != cudaSuccess) return err;
+    err = cudaMemsetAsync(bad, 0, sizeof(int), stream);
+    if (err != cudaSuccess) return err;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    quantize_insert_kernel<<<blocks, 256, 0, stream>>>(rows, stride, n, vs, keys, vals, slots - 1, bad);
+    quantize_keep_kernel<<<blocks, 256, 0, stream>>>(rows, stride, n, vs, keys, vals, slots - 1, keep);
+    return cudaGetLastError();
+}
+
+cudaError_t run_quantize_compact(const float *rows, int64_t stride, int cols, int64_t n, float vs, const uint8_t *keep,
+                                 const int32_t *prefix, float *out, int64_t out_stride, int32_t *cells, int64_t capacity,
+                                 cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const int64_t warps = (n + 31) / 32;
+    const unsigned blocks = (unsigned)((warps + (kSelThreads / kWarp) - 1) / (kSelThreads / kWarp));
+    quantize_compact_kernel<<<blocks, kSelThreads, 0, stream>>>(rows, stride, cols, n, vs, keep, prefix, out, out_stride, cells,
+                                                                capacity);
+    return cudaGetLastError();
+}
+
+}  // namespace cnrma

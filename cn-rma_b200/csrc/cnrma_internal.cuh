@@ -66,6 +66,13 @@ cudaError_t run_select_rows(const float *rows, int64_t row_stride, int cols, int
                             const int32_t *prefix, const float *offset3_host, float *out, int64_t out_stride,
                             int64_t capacity, cudaStream_t stream);
 
+size_t quantize_workspace_bytes(int64_t n);
+cudaError_t run_quantize_mark(const float *rows, int64_t stride, int64_t n, float vs, void *workspace, uint8_t *keep,
+                              cudaStream_t stream);
+cudaError_t run_quantize_compact(const float *rows, int64_t stride, int cols, int64_t n, float vs, const uint8_t *keep,
+                                 const int32_t *prefix, float *out, int64_t out_stride, int32_t *cells, int64_t capacity,
+                                 cudaStream_t stream);
+
 size_t sample_workspace_bytes();
 cudaError_t run_sample_mask(int64_t n, int64_t k, unsigned long long seed, void *workspace, uint8_t *mask,
                             cudaStream_t stream, const long long *n_dev = nullptr);

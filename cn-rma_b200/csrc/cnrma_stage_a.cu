@@ -46,11 +46,21 @@ struct AggParams {
     SweepOrder sweep;             // traversal order of the voxels
     int bilinear;                 // opt-in variant: four neighbouring rows per visible view
     int reserve_ctas;             // host only: CTA slots left free for a kernel that runs beside this one
+    int cull;                     // work unit = a column of the slab with per-column view culling (else one voxel)
     OutputRoute route;            // view-sharded output over peer memory (n_owners == 0: plain output)
     const void *views[kMaxViewsPerLaunch];
 };
 
 constexpr int kMaxChunkBytes = 1024;     // 64 16-byte vectors: two per lane
+
+// bytes in front of the row buffers: mbarriers, per-view pointers, camera matrices [12][Vpad], cull coefficients
+// [5][Vpad], per-warp candidate-view lists (uint16 [Vpad + 1] each)
+__host__ __device__ inline size_t agg_head_bytes(int V) {
+    const int Vpad = V | 1;
+    const size_t warps = kAggThreads / kWarp;
+    return (8 * warps + sizeof(void *) * V + sizeof(float) * 17 * Vpad + sizeof(uint16_t) * warps * (Vpad + 1) + 127) &
+           ~(size_t)127;
+}
 constexpr int kWarpBufferBytes = 6144;   // per-warp row buffer: 4 CTAs x 8 warps x 6 KB = 192 KB per SM
 constexpr int kAggCtasPerSm = 4;
 
@@ -69,9 +79,11 @@ aggregate_views_kernel(const __grid_constant__ AggParams p) {
     uint64_t *sBar = reinterpret_cast<uint64_t *>(smem_raw);                                   // [kWarps]
     const unsigned char **sView = reinterpret_cast<const unsigned char **>(smem_raw + 8 * kWarps);   // [V]
     float *sP = reinterpret_cast<float *>(smem_raw + 8 * kWarps + sizeof(void *) * p.V);       // [12][Vpad]
-    const size_t head = (8 * kWarps + sizeof(void *) * p.V + sizeof(float) * 12 * Vpad + 127) & ~(size_t)127;
+    float *sCull = sP + 12 * Vpad;                                                             // [5][Vpad]
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    uint16_t *sCand = reinterpret_cast<uint16_t *>(sCull + 5 * Vpad) + (size_t)warp * (Vpad + 1);   // [kWarps][Vpad + 1]
+    const size_t head = agg_head_bytes(p.V);
     unsigned char *rowbuf = smem_raw + head + (size_t)warp * p.rows_cap * p.chunk_bytes;
     float *wbuf = reinterpret_cast<float *>(smem_raw + head + (size_t)kWarps * p.rows_cap * p.chunk_bytes) + warp * p.rows_cap;   // BILINEAR: weight per slot
 
@@ -87,6 +99,18 @@ aggregate_views_kernel(const __grid_constant__ AggParams p) {
     if (threadIdx.x < kWarps) mbar_init(smem_u32(&sBar[threadIdx.x]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
+    // View culling per voxel column (see the main loop): how fast the five frustum forms of rm.py:58 can grow along z,
+    // per view, in world units -- |d/dz| of  cx + cz/2,  (W - 1/2) cz - cx,  cy + cz/2,  (H - 1/2) cz - cy,  cz.
+    const float fW = (float)p.W - 0.5f, fH = (float)p.H - 0.5f;
+    for (int v = threadIdx.x; v < p.V; v += blockDim.x) {
+        const float px = sP[2 * Vpad + v], py = sP[6 * Vpad + v], pz = sP[10 * Vpad + v];
+        sCull[0 * Vpad + v] = fabsf(px + 0.5f * pz);
+        sCull[1 * Vpad + v] = fabsf(fW * pz - px);
+        sCull[2 * Vpad + v] = fabsf(py + 0.5f * pz);
+        sCull[3 * Vpad + v] = fabsf(fH * pz - py);
+        sCull[4 * Vpad + v] = fabsf(pz);
+    }
+    __syncthreads();
 
     const uint32_t bar = smem_u32(&sBar[warp]);
     const uint32_t buf0 = smem_u32(rowbuf);
@@ -95,16 +119,68 @@ aggregate_views_kernel(const __grid_constant__ AggParams p) {
     const int esz = (int)sizeof(T);
     uint32_t parity = 0;
 
+    // The voxels are visited in the order of SweepOrder (cnrma_common.cuh: slabs of T z-slices, x slow, then y, then the
+    // slab's z); all resident warps sweep the volume together, so repeated gathers of a pixel's row fall inside the L2
+    // residency window.  Two granularities (p.cull, chosen on the host):
+    //   voxel units   a warp takes one voxel at a time and projects it through every view (lane <-> view, 32 at a time).
+    //   column units  a warp takes one (x, y) column of a slab -- up to T voxels that differ in z only -- and first culls
+    //                 the views: a conservative form of the frustum test of rm.py:58 on the UN-divided camera coordinates
+    //                 of the column's centre, widened by how far each form can move over the column (sCull); a view
+    //                 that fails it sees none of the column's voxels.  The exact projection then runs over the surviving
+    //                 views only (in view order): for 50 ring cameras ~20 survive, one lane round instead of two.
+    //                 Fewer instructions per voxel, but the voxels in flight span T times more columns: it pays on fine
+    //                 grids, where a pixel's row is gathered ~20 times and the L2 window is lost anyway (cfg 4: 2.08 ->
+    //                 1.89 ms), not where the window just fits (cfg 2: 0.286 -> 0.313 ms); profiles/r02_kernels.md.
     const int warps_total = gridDim.x * kWarps;
-    for (int it = blockIdx.x * kWarps + warp; it < p.nvox; it += warps_total) {
-        // Traversal order: slabs of a few z-slices (SweepOrder in cnrma_common.cuh): all resident warps sweep the
-        // volume together, and repeated gathers of a pixel's row fall inside the L2 residency window more often.
-        int vx, vy, vz;
-        sweep_voxel(p.sweep, it, vx, vy, vz);
-        // voxel order of datasets/tsdf.py:24-29: flat = (x*ny + y)*nz + z
-        const int vox = (vx * p.g.ny + vy) * p.g.nz + vz;
+    const int columns = p.g.nx * p.g.ny;
+    const int nslabs = p.sweep.nfull + (p.sweep.nfull * p.sweep.T < p.g.nz ? 1 : 0);
+    const float inv_columns = 1.0f / (float)columns;
+    // Every warp takes the same number of whole columns, round-robin; the columns left over after the last full round
+    // are dealt out voxel by voxel (one-voxel units), so that no warp runs a whole column longer than the others.
+    const int total_columns = columns * nslabs;
+    const int full_columns = p.cull ? (total_columns / warps_total) * warps_total : 0;
+    const int total_units = full_columns + (total_columns - full_columns) * p.sweep.T;
+    for (int u = blockIdx.x * kWarps + warp; u < total_units; u += warps_total) {
+        int col = u, zfirst = 0, zcount = p.sweep.T;
+        if (u >= full_columns) {
+            fast_divmod(u - full_columns, p.sweep.T, p.sweep.inv_T, col, zfirst);
+            col += full_columns;
+            zcount = 1;
+        }
+        int slab, xy, vx, vy;
+        fast_divmod(col, columns, inv_columns, slab, xy);
+        fast_divmod(xy, p.g.ny, p.sweep.inv_ny, vx, vy);
+        const int z0 = slab * p.sweep.T + zfirst;
+        const int nzu = min(zcount, p.g.nz - z0);     // <= 0: a one-voxel unit beyond the last (thinner) slab
+        if (nzu <= 0) continue;
         const float wx = world_coord(vx + p.g.x0, p.g.vs, p.g.ox);
         const float wy = world_coord(vy + p.g.y0, p.g.vs, p.g.oy);
+        const float rho = 0.5f * (float)(nzu - 1) * p.g.vs;                          // half the column's length
+        const float wzc = ((float)(z0 + p.g.z0) + 0.5f * (float)(nzu - 1)) * p.g.vs + p.g.oz;   // its centre (cull only)
+        int ncand = p.cull ? 0 : p.V;
+        for (int v0 = 0; v0 < p.V && p.cull; v0 += 32) {
+            const int view = v0 + lane;
+            bool maybe = false;
+            if (view < p.V) {
+                const float *P = sP + view;
+                const float cx = row_dot4(P[0 * Vpad], P[1 * Vpad], P[2 * Vpad], P[3 * Vpad], wx, wy, wzc, 1.0f);
+                const float cy = row_dot4(P[4 * Vpad], P[5 * Vpad], P[6 * Vpad], P[7 * Vpad], wx, wy, wzc, 1.0f);
+                const float cz = row_dot4(P[8 * Vpad], P[9 * Vpad], P[10 * Vpad], P[11 * Vpad], wx, wy, wzc, 1.0f);
+                const float *Q = sCull + view;
+                const float slack = 1.0e-3f * (fabsf(cz) + rho * Q[4 * Vpad]);      // rounding of the fp32 chains: ~1e-6
+                maybe = (cz + rho * Q[4 * Vpad] >= -slack) && (cx + 0.5f * cz + rho * Q[0 * Vpad] >= -slack) &&
+                        (fW * cz - cx + rho * Q[1 * Vpad] >= -slack) && (cy + 0.5f * cz + rho * Q[2 * Vpad] >= -slack) &&
+                        (fH * cz - cy + rho * Q[3 * Vpad] >= -slack);
+            }
+            const unsigned mb = __ballot_sync(0xffffffffu, maybe);
+            if (maybe) sCand[ncand + __popc(mb & ((1u << lane) - 1u))] = (uint16_t)view;
+            ncand += __popc(mb);
+        }
+        __syncwarp();
+      for (int zi = 0; zi < nzu; ++zi) {
+        const int vz = z0 + zi;
+        // voxel order of datasets/tsdf.py:24-29: flat = (x*ny + y)*nz + z
+        const int vox = (vx * p.g.ny + vy) * p.g.nz + vz;
         const float wz = world_coord(vz + p.g.z0, p.g.vs, p.g.oz);
 
         float acc[VPL][E];
@@ -165,12 +241,12 @@ aggregate_views_kernel(const __grid_constant__ AggParams p) {
             __syncwarp();   // all lanes are done reading before the slots are overwritten
         };
 
-        for (int v0 = 0; v0 < p.V; v0 += 32) {
-            const int view = v0 + lane;
+        for (int v0 = 0; v0 < ncand; v0 += 32) {
+            const int view = (v0 + lane < ncand) ? (p.cull ? (int)sCand[v0 + lane] : v0 + lane) : -1;   // ascending: slot order == view order
             int64_t off = -1;
             int64_t off4[4] = {0, 0, 0, 0};
             float w4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            if (view < p.V) {
+            if (view >= 0) {
                 if (BILINEAR) {
                     const float *P = sP + view;
                     const float cx = row_dot4(P[0 * Vpad], P[1 * Vpad], P[2 * Vpad], P[3 * Vpad], wx, wy, wz, 1.0f);
@@ -259,6 +335,8 @@ aggregate_views_kernel(const __grid_constant__ AggParams p) {
             else p.count[vox] = cnt;
             if (p.valid != nullptr) p.valid[vox] = (uint8_t)(cnt > 0);
         }
+      }            // voxels of the column
+        __syncwarp();   // the candidate list is rewritten by the next column
     }
 }
 
@@ -275,8 +353,7 @@ static int plan_chunk_bytes(int row_bytes, int max_chunk_bytes) {
 
 template <int VPL, typename T, bool BILINEAR = false>
 static cudaError_t launch_agg(const AggParams &p, int chunks, cudaStream_t stream) {
-    const int Vpad = p.V | 1;
-    const size_t head = (8 * (kAggThreads / kWarp) + sizeof(void *) * p.V + sizeof(float) * 12 * Vpad + 127) & ~(size_t)127;
+    const size_t head = agg_head_bytes(p.V);
     const size_t smem = head + (size_t)(kAggThreads / kWarp) * p.rows_cap * (p.chunk_bytes + (BILINEAR ? sizeof(float) : 0));
     auto kernel = aggregate_views_kernel<VPL, T, BILINEAR>;
     // launch configuration cached per (kernel instantiation, device, smem size): the attribute / occupancy queries
@@ -300,7 +377,7 @@ static cudaError_t launch_agg(const AggParams &p, int chunks, cudaStream_t strea
     }
     int persistent = cache.ctas - p.reserve_ctas;
     if (persistent < 1) persistent = 1;
-    const int needed = (p.nvox + (kAggThreads / kWarp) - 1) / (kAggThreads / kWarp);
+    const int needed = (p.nvox + (kAggThreads / kWarp) - 1) / (kAggThreads / kWarp);   // at least one voxel per warp
     const dim3 grid(needed < persistent ? needed : persistent, chunks);
     kernel<<<grid, kAggThreads, smem, stream>>>(p);
     return cudaGetLastError();
@@ -392,6 +469,10 @@ cudaError_t run_aggregate_views(const GridDev &g, const cnrma_features &f, int v
     p.reserve_ctas = reserve_ctas > 0 ? reserve_ctas : 0;
     p.flags = flags & ~kAggBilinearInternal;
     p.sweep = make_sweep(g.nx, g.ny, g.nz, sweep_thickness(g.ny, g.nz, nv, row_bytes));
+    // column units + view culling where every pixel row is gathered many times over (see the kernel): about a quarter of
+    // the views see a voxel, so a row is gathered ~nvox / (4 H W) times
+    p.cull = (double)p.nvox >= 32.0 * f.height * f.width;
+    if (tuning().agg_cull >= 0) p.cull = tuning().agg_cull;   // CNRMA_AGG_CULL
     return run_aggregate(p, f.dtype, max_chunk_bytes, stream);
 }
 

@@ -874,6 +874,70 @@ def switch_pointcloud(points, offsets, max_points=None, masks=None, rng=None):
     return coords, feats
 
 
+def _rows_view(coords, feats):
+    """[N,3] coords and [N,C] features as one [N,3+C] row tensor: the buffer they are both views of when they come from
+    switch_pointcloud / rma_points_selected, else a concatenation."""
+    base = coords._base
+    if (base is not None and feats._base is base and base.dim() == 2 and base.is_contiguous()
+            and base.shape[1] == 3 + feats.shape[1] and coords.data_ptr() == base.data_ptr()
+            and feats.data_ptr() == base.data_ptr() + 3 * base.element_size() and coords.shape[0] <= base.shape[0]):
+        return base[: coords.shape[0]]
+    return torch.cat((coords, feats), dim=1).contiguous()
+
+
+def quantize_points(coords, feats, voxel_size, batch_index=None):
+    """The data side of `ME.utils.batch_sparse_collate` + `ME.SparseTensor` for ONE batch element (rm.py:330-332;
+    MinkowskiEngine 0.5.4 is not part of the reference tree): cells = trunc(coords / voxel_size) as int32, one row per
+    occupied cell -- the first in row order, survivors in row order (MinkowskiEngine keeps an arbitrary duplicate; this
+    is the deterministic choice).  coords [N,3] float32 CUDA (the reference passes the un-divided coordinates and
+    divides in the call, rm.py:331), feats [N,C].
+    Returns (cells int32 [K,3] -- or [K,4] with `batch_index` in column 0, as sparse_collate lays them out --,
+    features [K,C], coords [K,3])."""
+    lib = _lib.load()
+    if not coords.is_cuda or coords.dtype != torch.float32 or feats.dtype != torch.float32:
+        raise CnrmaError("coords / feats must be float32 CUDA tensors")
+    if torch.is_grad_enabled() and (coords.requires_grad or feats.requires_grad):
+        raise CnrmaError("quantize_points has no backward: quantise detached tensors (MinkowskiEngine re-attaches the "
+                         "features it keeps through its own index)")
+    device = coords.device
+    rows = _rows_view(coords.detach(), feats.detach())
+    n, cols = rows.shape
+    lead = 0 if batch_index is None else 1
+    if n == 0:
+        return (torch.zeros((0, 3 + lead), dtype=torch.int32, device=device), rows[:, 3:], rows[:, :3])
+    with torch.cuda.device(device):
+        nbytes = C.c_size_t(0)
+        _lib.check(lib.cnrma_quantize_workspace_bytes(n, C.byref(nbytes)), "cnrma_quantize_workspace_bytes")
+        ws = _lib.empty(nbytes.value, dtype=torch.uint8, device=device)
+        keep = _lib.empty(n, dtype=torch.bool, device=device)
+        _lib.check(lib.cnrma_quantize_mark(C.c_void_p(rows.data_ptr()), rows.stride(0), n, float(voxel_size),
+                                           C.c_void_p(ws.data_ptr()), nbytes.value, C.c_void_p(keep.data_ptr()),
+                                           _stream(device)), "cnrma_quantize_mark")
+        prefix, kept = _mask_prefix(keep)
+        k = int(kept.item())                                    # the one host sync: the number of occupied cells
+        out = _lib.empty((k, cols), dtype=torch.float32, device=device)
+        cells = _lib.empty((k, 3), dtype=torch.int32, device=device)
+        if k > 0:
+            _lib.check(lib.cnrma_quantize_compact(C.c_void_p(rows.data_ptr()), rows.stride(0), cols, n, float(voxel_size),
+                                                  C.c_void_p(keep.data_ptr()), C.c_void_p(prefix.data_ptr()),
+                                                  C.c_void_p(out.data_ptr()), cols, C.c_void_p(cells.data_ptr()), k,
+                                                  _stream(device)), "cnrma_quantize_compact")
+    if batch_index is not None:
+        cells = torch.cat((torch.full((k, 1), int(batch_index), dtype=torch.int32, device=device), cells), dim=1)
+    return cells, out[:, 3:], out[:, :3]
+
+
+def sparse_collate_quantized(coords_list, feats_list, voxel_size):
+    """Drop-in for the data preparation of rm.py:330-332 over the batch: returns (coordinates int32 [K,4] with the batch
+    index in column 0, features [K,C]) ready for `ME.SparseTensor(coordinates=..., features=...)`, already unique."""
+    cells, feats = [], []
+    for b, (c, f) in enumerate(zip(coords_list, feats_list)):
+        q, ff, _c = quantize_points(c, f, voxel_size, batch_index=b)
+        cells.append(q)
+        feats.append(ff)
+    return torch.cat(cells, dim=0), torch.cat(feats, dim=0)
+
+
 def _selected_without_sync(lib, fs, m, grid, desc, cap, max_points, seed, off, cols, device):
     """Sampler (row count from the march's result block on the device), prefix sum and selected fill for at most `cap`
     rows, queued without reading M: returns the [max_points, cols] buffer whose first min(M, max_points) rows are valid

@@ -310,6 +310,21 @@ int cnrma_sample_mask(int64_t rows, int64_t keep, uint64_t seed, void *workspace
 int cnrma_sample_mask_for_result(const cnrma_rma_result *result, int64_t capacity, int64_t keep, uint64_t seed,
                                  void *workspace, size_t workspace_bytes, uint8_t *mask, void *stream);
 
+/* The last step of the hand-off (rm.py:330-332): `coords / voxel_size_fcaf3d` goes into MinkowskiEngine 0.5.4
+ * (ME.utils.batch_sparse_collate + ME.SparseTensor; third-party, not part of the reference tree), whose collate step
+ * truncates the quotient to int32 and whose sparse tensor keeps one row per occupied cell.  These two calls do that on
+ * the device, deterministically: the FIRST row of every cell (in row order) survives, survivors stay in row order.
+ *   cnrma_quantize_mark     keep[i] = 1 iff row i is the first row of its cell trunc(coord / voxel_size); rows whose cell
+ *                           index leaves +-2^20 on an axis (or is NaN) are dropped.  workspace: cnrma_quantize_workspace_bytes.
+ *   cnrma_quantize_compact  with prefix = exclusive prefix sum of keep (cnrma_mask_prefix): surviving rows copied whole to
+ *                           out[prefix[i]], their cells to cells[prefix[i]] (int32 [K,3]; may be NULL). */
+int cnrma_quantize_workspace_bytes(int64_t rows, size_t *bytes);
+int cnrma_quantize_mark(const float *rows, int64_t row_stride, int64_t n_rows, float voxel_size, void *workspace,
+                        size_t workspace_bytes, uint8_t *keep, void *stream);
+int cnrma_quantize_compact(const float *rows, int64_t row_stride, int cols, int64_t n_rows, float voxel_size,
+                           const uint8_t *keep, const int32_t *prefix, float *out, int64_t out_stride, int32_t *cells,
+                           int64_t capacity, void *stream);
+
 /* cnrma_rma_fill fused with the hand-off: only the kept rows are produced (at out row prefix[row], offset added),
  * i.e. aggregate_2d_features_ray_marching + switch_pointcloud in one pass.  mask / prefix index the M rows of the
  * march in their (view, v, u, step) order and hold `mask_rows` entries: rows beyond them are dropped (0: they cover

@@ -270,3 +270,17 @@ def tsdf_head(xs, weights, label_smoothing, sparse_threshold):
             masks.append(m)
         prev = t
     return out, masks
+
+
+def quantize_unique_first(coords, feats, voxel_size):
+    """The hand-off's quantisation (rm.py:330-332 + MinkowskiEngine 0.5.4, which is NOT in the reference tree: its
+    published behaviour is restated here and parity with ME itself is unpinned).  `ME.utils.batch_sparse_collate`
+    stores `coords / voxel_size_fcaf3d` -- a float32 tensor divided by a Python float, i.e. IEEE float32 division on CPU --
+    into an int32 tensor (truncation toward zero), and `ME.SparseTensor` keeps one row per distinct coordinate.  Which
+    duplicate survives is unspecified there; the contract here is the first in row order, survivors in row order.
+    Returns (cells int32 [K,3], feats [K,C], coords [K,3])."""
+    c = _f(coords)
+    q = np.trunc(c / np.float32(voxel_size)).astype(np.int32)
+    _, first = np.unique(q, axis=0, return_index=True)
+    first = np.sort(first)
+    return q[first], _f(feats)[first], c[first]

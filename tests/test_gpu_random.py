@@ -58,6 +58,28 @@ def test_random_scene(seed):
     assert np.abs(rows[:, 3] - ref[:, 3]).max() <= 1e-5 * max(ref[:, 3].max(), 1e-3)
 
 
+@pytest.mark.parametrize("seed", range(int(os.environ.get("CNRMA_RANDOM_SEEDS", "24"))))
+@pytest.mark.parametrize("slab", [None, "1", "5"])
+def test_random_scene_stage_a_with_view_culling(seed, slab, monkeypatch):
+    """The TMA gather kernel in column units: a conservative per-column cull of the views, then the exact projection over
+    the survivors.  Random cameras (outside the grid, looking away, singular-ish intrinsics) and column lengths: a view
+    that is culled wrongly would change a count or a sum."""
+    import cnrma_b200 as cn
+    monkeypatch.setenv("CNRMA_AGG_KERNEL", "tma")
+    monkeypatch.setenv("CNRMA_AGG_CULL", "1")
+    if slab is not None:
+        monkeypatch.setenv("CNRMA_AGG_SLAB", slab)
+    s = _random_scene(np.random.default_rng(3000 + seed))
+    f = torch.from_numpy(s["feats"]).cuda().unsqueeze(1).permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+    p = torch.from_numpy(s["projs"]).cuda().unsqueeze(1)
+    args = (s["dim"], s["vs"], s["origin"], s["stride"])
+    for mean in (False, True):
+        ovol, ocnt = oracle.aggregate_views(s["projs"], s["feats"], *args, mean=mean)
+        vol, cnt, _ = cn.aggregate_views(p, f, *args, mean=mean)
+        assert np.array_equal(cnt[0, 0].cpu().numpy(), ocnt)
+        assert np.array_equal(vol[0].cpu().numpy().view(np.uint32), ovol.view(np.uint32))
+
+
 @pytest.mark.parametrize("seed", range(8))
 def test_random_fusion(seed):
     """GT TSDF fusion kernel against the oracle on random frame sets (half frame by frame, half in one launch)."""

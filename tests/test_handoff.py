@@ -99,3 +99,54 @@ def test_device_sampler_properties():
     pts = torch.randn(n, 7, device="cuda")
     coords, feats = cn.switch_pointcloud([pts], [[0.0, 0.0, 0.0]], masks=[m1])
     assert torch.equal(torch.cat((coords[0], feats[0]), 1), pts[m1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,c,scale", [(1, 4, 1.0), (5000, 8, 0.05), (200000, 32, 0.4), (70000, 259 - 3, 2.0)])
+def test_quantize_points_keeps_the_first_row_of_every_cell(n, c, scale):
+    """rm.py:330-332 + MinkowskiEngine's collate / unique: cells = trunc(coords / 0.01), first row of every cell in row
+    order -- bit-exact against the numpy restatement (oracle.quantize_unique_first), duplicates, negative coordinates
+    and cell boundaries included."""
+    import cnrma_b200 as cn
+    import oracle
+    rng = np.random.default_rng(n)
+    coords = (rng.standard_normal((n, 3)) * scale).astype(np.float32)
+    coords[::7] = coords[::7].round(2)                        # values on cell boundaries
+    if n > 10:
+        coords[n // 2:] = coords[: n - n // 2] + rng.uniform(-0.004, 0.004, size=(n - n // 2, 3)).astype(np.float32)  # near-duplicates
+        coords[3] = [-0.0, 0.0, -0.0099]
+    feats = rng.standard_normal((n, c)).astype(np.float32)
+    want_q, want_f, want_c = oracle.quantize_unique_first(coords, feats, 0.01)
+    rows = torch.from_numpy(np.concatenate([coords, feats], 1)).cuda()
+    for cd, fd in ((rows[:, :3], rows[:, 3:]),                                       # views of one row buffer
+                   (torch.from_numpy(coords).cuda(), torch.from_numpy(feats).cuda())):   # separate tensors
+        q, f, cc = cn.quantize_points(cd, fd, 0.01)
+        assert np.array_equal(q.cpu().numpy(), want_q)
+        assert np.array_equal(f.cpu().numpy().view(np.uint32), want_f.view(np.uint32))
+        assert np.array_equal(cc.cpu().numpy().view(np.uint32), want_c.view(np.uint32))
+    assert want_q.shape[0] < n or n <= 10
+    coords4, feats_cat = cn.sparse_collate_quantized([rows[:, :3], rows[:, :3] + 1.0], [rows[:, 3:], rows[:, 3:]], 0.01)
+    assert coords4.shape[1] == 4 and int(coords4[:, 0].max()) == 1 and coords4.shape[0] == feats_cat.shape[0]
+    assert np.array_equal(coords4[: want_q.shape[0], 1:].cpu().numpy(), want_q)
+
+
+@pytest.mark.gpu
+def test_quantize_points_on_the_golden_hand_off(golden):
+    """The reference's own switch_pointcloud output (golden vectors), quantised: device == numpy restatement."""
+    import cnrma_b200 as cn
+    import oracle
+    coords, feats = golden["handoff_coords"], golden["handoff_features"]
+    want_q, want_f, _ = oracle.quantize_unique_first(coords, feats, 0.01)
+    q, f, _ = cn.quantize_points(torch.from_numpy(coords).cuda(), torch.from_numpy(feats).cuda(), 0.01)
+    assert np.array_equal(q.cpu().numpy(), want_q) and np.array_equal(f.cpu().numpy(), want_f)
+
+
+def test_quantize_restatement_properties():
+    """CPU: the numpy restatement itself -- truncation toward zero, first occurrence wins, order kept."""
+    import oracle
+    coords = np.array([[0.019, -0.019, 0.0], [0.011, -0.011, 0.009], [0.5, 0.5, 0.5], [-0.005, 0.005, 0.0],
+                       [0.5001, 0.5, 0.5]], np.float32)
+    feats = np.arange(5, dtype=np.float32)[:, None]
+    q, f, c = oracle.quantize_unique_first(coords, feats, 0.01)
+    assert q.tolist() == [[1, -1, 0], [50, 50, 50], [0, 0, 0]]      # (-0.5 .. 0.5) truncates to 0; rows 1 and 4 are duplicates
+    assert f[:, 0].tolist() == [0.0, 2.0, 3.0]
