@@ -147,7 +147,7 @@ static int aggregate_views_impl(const cnrma_grid *grid, const cnrma_box *box, co
     // overhead of the TMA kernel on rows below 512 bytes.
     int batch = kMaxViewsPerLaunch;
     const int row_bytes = features->channels * (features->dtype == CNRMA_BF16 ? 2 : 4);
-    if (row_bytes < 512 && features->views > kListViewsMax) {
+    if (row_bytes < 512 && features->views > kListViewsMax && !long_list_supports(features->channels, features->dtype)) {
         const int per = tuning().agg_list_views > 0 ? tuning().agg_list_views : kListViewsBatch;   // tuning aid
         if (per >= 1 && per <= kListViewsMax) {
             const int nbatch = (features->views + per - 1) / per;

@@ -23,6 +23,7 @@ cudaError_t run_aggregate_views(const GridDev &g, const cnrma_features &f, int v
                                 int64_t vsc, int32_t *count, uint8_t *valid, int max_chunk_bytes, cudaStream_t stream,
                                 const OutputRoute *route = nullptr, int reserve_ctas = 0);
 bool list_kernel_supports(int V, int H, int W);
+bool long_list_supports(int channels, int dtype);
 cudaError_t run_aggregate_list(const GridDev &g, const cnrma_features &f, int v0, int nv, const float *proj,
                                int64_t proj_stride, float stride, uint32_t flags, float *volume, int64_t vsv, int64_t vsc,
                                int32_t *count, uint8_t *valid, cudaStream_t stream, const OutputRoute *route = nullptr,

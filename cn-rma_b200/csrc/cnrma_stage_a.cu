@@ -431,7 +431,8 @@ cudaError_t run_aggregate_views(const GridDev &g, const cnrma_features &f, int v
     // (cnrma_stage_a_list.cu), whose lane <-> voxel projection needs a third of the instructions.
     const int row_bytes = f.channels * ((f.dtype == CNRMA_BF16) ? 2 : 4);
     // (beyond ~96 views the per-voxel lists no longer fit 32 voxels per warp and the list kernel loses its edge)
-    bool use_list = ((row_bytes < 512 && nv <= kListViewsMax) || nv == 0) && !(flags & kAggBilinearInternal);
+    bool use_list = ((row_bytes < 512 && (nv <= kListViewsMax || (route == nullptr && long_list_supports(f.channels, f.dtype)))) ||
+                     nv == 0) && !(flags & kAggBilinearInternal);
     if (tuning().agg_kernel >= 0) use_list = (tuning().agg_kernel == 1) && !(flags & kAggBilinearInternal);   // CNRMA_AGG_KERNEL
     if (use_list && list_kernel_supports(nv, f.height, f.width))
         return run_aggregate_list(g, f, v0, nv, proj, proj_stride, stride, flags, volume, vsv, vsc, count, valid, stream, route,

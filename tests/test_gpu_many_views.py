@@ -80,3 +80,37 @@ def test_backward_over_512_views_matches_split_runs(cn, wide):
     assert float(ref_a.abs().max()) > 0 and float(ref_b.abs().max()) > 0
     assert float((ga - ref_a).abs().max()) <= 1e-5 * float(ref_a.abs().max())      # fp32 reductions in the memory system
     assert torch.equal(gb, ref_b)                                                    # per-ray sums: no atomics
+
+
+@pytest.mark.parametrize("channels,dtype", [(16, torch.float32), (32, torch.float32), (48, torch.float32), (64, torch.bfloat16),
+                                            (96, torch.float32)])
+def test_stage_a_long_lists_with_segments(cn, channels, dtype):
+    """Short rows and hundreds of views: the long-list Stage A kernel (all views of a voxel in one go).  Every camera
+    looks at the same small grid, so many voxels are seen by more views than a list holds (161) and are served in
+    segments through the volume; also as two accumulating calls, and on a box.  Bit-exact against the oracle."""
+    views = 400
+    sc = cn.synthetic.make_scene(dict(views=views, channels=channels, height=6, width=8, voxel_dim=(11, 9, 5),
+                                      voxel_size=0.5, tsdf="room", grids=40, dtype="f32"), seed=8)
+    p = torch.from_numpy(sc.projections).cuda().unsqueeze(1)
+    f = torch.from_numpy(sc.features).cuda().to(dtype).unsqueeze(1).permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+    feats_host = f[:, 0].float().contiguous().cpu().numpy()
+    args = (sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
+    for mean in (True, False):
+        ovol, ocnt = oracle.aggregate_views(sc.projections, feats_host, *args, mean=mean)
+        assert int(ocnt.max()) > 200
+        vol, cnt, valid = cn.aggregate_views(p, f, *args, mean=mean)
+        assert np.array_equal(cnt[0, 0].cpu().numpy(), ocnt)
+        assert np.array_equal(valid[0, 0].cpu().numpy(), ocnt > 0)
+        assert np.array_equal(vol[0].cpu().numpy().view(np.uint32), ovol.view(np.uint32)), (channels, mean)
+    # two accumulating calls (the second starts from sums and counts in the volume), then the mean
+    out = cn.aggregate_views(p[:170], f[:170], *args, mean=False)
+    vol2, cnt2, _ = cn.aggregate_views(p[170:], f[170:], *args, mean=True, out=out)
+    ovol, ocnt = oracle.aggregate_views(sc.projections, feats_host, *args, mean=True)
+    assert np.array_equal(cnt2[0, 0].cpu().numpy(), ocnt)
+    assert np.array_equal(vol2[0].cpu().numpy().view(np.uint32), ovol.view(np.uint32))
+    # a box of the grid
+    lo, dim = (2, 1, 1), (7, 6, 3)
+    bv, bc, _ = cn.aggregate_views(p, f, *args, mean=True, box=(lo, dim))
+    sl = tuple(slice(l, l + d) for l, d in zip(lo, dim))
+    assert np.array_equal(bc[0, 0].cpu().numpy(), ocnt[sl])
+    assert np.array_equal(bv[0].contiguous().cpu().numpy().view(np.uint32), np.ascontiguousarray(ovol[(slice(None),) + sl]).view(np.uint32))
