@@ -452,6 +452,12 @@ def main():
                           "launch / host-sync gaps of the phase); bytes use the mean row count of the rotated scenes",
                 "stage_a_frac": kernels["aggregate_views_kernel"]["gbs"] / hbm_peak if ms_a else None,
                 "stage_a_traffic": traffic.get("aggregate_views_kernel")}
+    if traffic.get("_fill_rows") and dom == "fill_rows_tma_kernel":
+        # the ncu capture ran ONE scene (seed 0): its row count and the algorithmic bytes of that launch, so that
+        # `traffic` is compared with the bytes of the launch it was measured on, not with the mean over the rotated scenes
+        m0 = traffic["_fill_rows"]
+        roofline["traffic_rows"] = m0
+        roofline["traffic_algorithmic_bytes"] = m0 * (3 + C) * 4 + V * H * W * C * esz + m0 * 8 + V * H * W * 4
 
     value = world * sc.voxel_views / (ms_step * 1e-3)
 
@@ -459,6 +465,8 @@ def main():
     e2e = None
     if not args.no_e2e and args.stage == "both":
         e2e = run_e2e(args, cn, scenes, dev, world, max(rows_seen))
+        if world > 1:                                       # one probe of the host's copy ceiling beside the number
+            e2e["host_copy_ceiling"] = host_copy_probe(dev, world)
 
     # --- the view-sharded forms of ONE large scene (BASELINE config 4), N > 1 only ------------------------------
     view_sharded = None
@@ -683,6 +691,43 @@ def run_view_sharded(args, cn, dev, rank, world):
         dist.destroy_process_group()
 
 
+def host_copy_probe(dev, world, mb=512):
+    """What the host lets this rank copy while every rank copies at once: pinned H2D alone, D2H alone and both together
+    (GB/s, two streams).  The e2e leg moves ~1 GB in and ~7 GB out per scene and rank, so at N ranks it is bounded by
+    these figures, not by the kernels (profiles/r02_multi_gpu.md holds the 1/2/4/8-rank table of this pool's box)."""
+    import torch
+    import torch.distributed as dist
+    n = mb * 1024 * 1024
+    h_in, h_out = torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_in, d_out = torch.empty(n, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def run(h2d, d2h, reps=3):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        s1.wait_event(a)
+        s2.wait_event(a)
+        for _ in range(reps):
+            if h2d:
+                with torch.cuda.stream(s1):
+                    d_in.copy_(h_in, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.current_stream().wait_stream(s1)
+        torch.cuda.current_stream().wait_stream(s2)
+        b.record()
+        torch.cuda.synchronize()
+        return (int(h2d) + int(d2h)) * reps * n / a.elapsed_time(b) / 1e6
+
+    run(True, True, 1)
+    return {"ranks_copying": world, "h2d_gbs": run(True, False), "d2h_gbs": run(False, True),
+            "both_total_gbs": run(True, True), "what": "per-rank pinned-copy rates of rank 0 while all ranks copy"}
+
+
 def run_e2e(args, cn, scenes, dev, world, max_rows, handoff_rows=None):
     """The same step through the stateful host mirror of the reference detector's aggregation methods
     (cn.RayMarchingAggregator) with HOST buffers: every step copies its scene's inputs from pinned host memory to the
@@ -697,15 +742,16 @@ def run_e2e(args, cn, scenes, dev, world, max_rows, handoff_rows=None):
     V, C, H, W = sc.views, sc.channels, sc.height, sc.width
     nx, ny, nz = sc.voxel_dim
     hosts = []
-    for s_ in scenes[:2]:                                   # two host scenes alternate (pinned, like a dataloader's)
+    for s_ in scenes[:2 if world < 4 else 1]:               # host scenes alternate (pinned, like a dataloader's)
         f = s_["feats"]
         h_feats = torch.empty(f.permute(0, 1, 3, 4, 2).shape, dtype=f.dtype).pin_memory()
         h_feats.copy_(f.permute(0, 1, 3, 4, 2))
         hosts.append(dict(feats=h_feats, proj=s_["proj_host"].pin_memory(), tsdf=s_["tsdf"].cpu().pin_memory()))
+    # one pinned result slot: the downloads of consecutive steps are ordered on the copy-out stream, and nobody reads
+    # the host copy in between (8 ranks x 8 GB of pinned rows is what the host can spare)
     outs = [dict(vol=torch.empty((1, nx, ny, nz, C), dtype=torch.float32).pin_memory(),
                  cnt=torch.empty((1, 1, nx, ny, nz), dtype=torch.int32).pin_memory(),
-                 pts=torch.empty((handoff_rows or int(max_rows * 1.07) + 2048, 3 + C), dtype=torch.float32).pin_memory(),
-                 free=torch.cuda.Event()) for _ in range(2)]
+                 pts=torch.empty((handoff_rows or int(max_rows) + 4096, 3 + C), dtype=torch.float32).pin_memory())]
     ag = cn.RayMarchingAggregator(sc.voxel_size, sc.voxel_dim, origin=sc.origin.tolist(), backbone2d_stride=sc.stride,
                                   neus_threshold=args.threshold)
     s_in, s_cmp, s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
@@ -724,7 +770,7 @@ def run_e2e(args, cn, scenes, dev, world, max_rows, handoff_rows=None):
             sl["loaded"].record(s_in)
 
     def compute_and_download(k):
-        sl, hs, out = slots[k % 2], hosts[k % len(hosts)], outs[k % 2]
+        sl, hs, out = slots[k % 2], hosts[k % len(hosts)], outs[0]
         with torch.cuda.stream(s_cmp):
             s_cmp.wait_event(sl["loaded"])
             d_feats = sl["feats"].permute(0, 1, 4, 2, 3)

@@ -88,7 +88,7 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
         objs = list(pool.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)

@@ -254,7 +254,10 @@ __device__ __forceinline__ VoxelMap make_voxel_map(const GridDev &g) {
 // Per-CTA totals: kept rows (the fill kernel works on the same blocks of kRayThreads consecutive rays) and the sum
 // of the kept weights (double, fixed shape -> deterministic).
 // (Mapping CTAs to 32x8-pixel tiles with 8x4-pixel warps instead of 256 consecutive rays was measured: no gain,
-// 336 -> 350 us on cfg 2 plus an extra block-count kernel, so rays stay in flat order.)
+// 336 -> 350 us on cfg 2 plus an extra block-count kernel, so rays stay in flat order.  Per-warp totals without the CTA
+// barrier -- ncu shows 16 % of the march's warp samples parked there, waiting for the block's longest ray -- were
+// measured too: the CTA keeps its slot until its last warp is done either way, and the single-CTA scan then walks eight
+// times as many partials: march phase 0.334 -> 0.375 ms on cfg 2, 0.504 -> 0.550 ms on the reference test grid.)
 template <int BLOCK>
 __device__ __forceinline__ void block_totals(int kept, double wsum, int32_t *blk_rows, double *blk_wsum) {
     __shared__ int s_rows[BLOCK / kWarp];

@@ -40,15 +40,18 @@ def main(path):
             if key in hdr:
                 i = hdr.index(key)
                 print(f"| {label} (`{key}`) | {r[i]} {units[i]} |")
+        # warp-state samples (smsp__pcsamp_warps_issue_stalled_*): where the resident warps spend their cycles
         stalls = []
         for i, h in enumerate(hdr):
-            if "warp_issue_stalled" in h and h.endswith("per_warp_active.pct"):
+            if h.startswith("smsp__pcsamp_warps_issue_stalled_") and not h.endswith("_not_issued"):
                 try:
-                    stalls.append((float(r[i]), h.replace("smsp__warp_issue_stalled_", "").replace("_per_warp_active.pct", "")))
+                    stalls.append((float(r[i]), h.replace("smsp__pcsamp_warps_issue_stalled_", "")))
                 except ValueError:
                     pass
+        total = sum(v for v, _ in stalls) or 1.0
         stalls.sort(reverse=True)
-        print("| top stall reasons (% of active warps) | " + ", ".join(f"{n} {v:.0f}" for v, n in stalls[:5]) + " |")
+        print("| warp states (% of pc samples; `selected` = issuing) | " +
+              ", ".join(f"{n} {100 * v / total:.0f}" for v, n in stalls[:7]) + " |")
         print()
 
 
