@@ -139,3 +139,58 @@ def test_torch_reference_medium(cn):
     ref.index_add_(0, ray_of_row, gp[:, 3:] * wn)
     ref = ref.view(sc.views, sc.height, sc.width, sc.channels).permute(0, 3, 1, 2)
     _close(f.grad[:, 0].cpu().numpy(), ref.cpu().numpy(), "stage B vs torch")
+
+
+def test_switch_pointcloud_backward(cn):
+    """forward_train's detection branch (rm.py:440-441): the loss on the selected points must reach the 2D features
+    through switch_pointcloud and rma_points.  Reference for the selection step: torch's own `points[mask]` + offset."""
+    sc = cn.synthetic.make_scene("small", seed=12)
+    f = torch.from_numpy(sc.features).cuda().unsqueeze(1).permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+    p = torch.from_numpy(sc.projections).cuda().unsqueeze(1)
+    t = torch.from_numpy(sc.tsdf).cuda()[None, None]
+    args = (sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
+    off = torch.tensor([0.25, -1.5, 0.125], device="cuda")
+    grads = []
+    for ours in (True, False):
+        ff = f.detach().clone().requires_grad_(True)
+        pts = cn.rma_points(p, ff, t, *args, grids=sc.grids, threshold=0.05)[0]
+        torch.manual_seed(3)
+        mask = torch.rand(pts.shape[0], device="cuda") < 0.3
+        if ours:
+            coords, feats = cn.switch_pointcloud([pts], [off], masks=[mask])
+            coords, feats = coords[0], feats[0]
+            assert coords.grad_fn is not None and feats.grad_fn is not None
+        else:
+            sel = pts[mask]
+            coords, feats = sel[:, :3] + off, sel[:, 3:]
+        gc = torch.randn(coords.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
+        gf = torch.randn(feats.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+        ((coords * gc).sum() + (feats * gf).sum()).backward()
+        assert float(ff.grad.abs().max()) > 0
+        grads.append(ff.grad.clone())
+    assert torch.equal(grads[0], grads[1])
+    # the fused, inference-only form refuses to run under autograd instead of dropping the gradient
+    with pytest.raises(cn.CnrmaError, match="no backward"):
+        cn.rma_points_selected(p, f.detach().clone().requires_grad_(True), t, *args, offsets=[[0.0, 0.0, 0.0]],
+                               max_points=100, device_seed=1, grids=sc.grids, threshold=0.05)
+
+
+def test_rma_points_selected_without_host_stall_matches_the_two_step_form(cn):
+    """device_seed: the mask is drawn from the row count in device memory and everything is queued before M is read;
+    the kept rows must equal sample_points_device's mask applied by switch_pointcloud, call after call (the first call
+    has no size guess and takes the synchronous path)."""
+    sc = cn.synthetic.make_scene("small", seed=13)
+    f = torch.from_numpy(sc.features).cuda().unsqueeze(1)
+    p = torch.from_numpy(sc.projections).cuda().unsqueeze(1)
+    t = torch.from_numpy(sc.tsdf).cuda()[None, None]
+    args = (sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
+    pts = cn.rma_points(p, f, t, *args, grids=sc.grids, threshold=0.05)[0]
+    n = pts.shape[0]
+    for keep in (1000, n + 5):
+        for call in range(3):
+            co, fe = cn.rma_points_selected(p, f, t, *args, offsets=[[1.0, 2.0, 3.0]], max_points=keep, device_seed=77,
+                                            grids=sc.grids, threshold=0.05)
+            mask = cn.sample_points_device(n, keep, 77, "cuda")
+            c2, f2 = cn.switch_pointcloud([pts], [[1.0, 2.0, 3.0]], masks=[mask])
+            assert co[0].shape[0] == min(keep, n)
+            assert torch.equal(co[0], c2[0]) and torch.equal(fe[0], f2[0]), (keep, call)
