@@ -58,8 +58,9 @@ constexpr int kMaxChunkBytes = 1024;     // 64 16-byte vectors: two per lane
 __host__ __device__ inline size_t agg_head_bytes(int V) {
     const int Vpad = V | 1;
     const size_t warps = kAggThreads / kWarp;
-    return (8 * warps + sizeof(void *) * V + sizeof(float) * 17 * Vpad + sizeof(uint16_t) * warps * (Vpad + 1) + 127) &
-           ~(size_t)127;
+    const size_t rounds = (V + 31) / 32;   // CTA-cooperative culling: two buffers of per-round survivor lists + counts
+    return (8 * warps + sizeof(void *) * V + sizeof(float) * 17 * Vpad + sizeof(uint16_t) * warps * (Vpad + 1) +
+            2 * rounds * (32 * sizeof(uint16_t) + sizeof(int)) + 8 + 127) & ~(size_t)127;
 }
 constexpr int kWarpBufferBytes = 6144;   // per-warp row buffer: 4 CTAs x 8 warps x 6 KB = 192 KB per SM
 constexpr int kAggCtasPerSm = 4;
@@ -83,6 +84,9 @@ aggregate_views_kernel(const __grid_constant__ AggParams p) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     uint16_t *sCand = reinterpret_cast<uint16_t *>(sCull + 5 * Vpad) + (size_t)warp * (Vpad + 1);   // [kWarps][Vpad + 1]
+    const int cull_rounds = (p.V + 31) >> 5;
+    uint16_t *sCandR = reinterpret_cast<uint16_t *>(sCull + 5 * Vpad) + (size_t)kWarps * (Vpad + 1);   // [2][rounds][32]
+    int *sCnt = reinterpret_cast<int *>((reinterpret_cast<uintptr_t>(sCandR + 2 * cull_rounds * 32) + 3) & ~(uintptr_t)3);   // [2][rounds]
     const size_t head = agg_head_bytes(p.V);
     unsigned char *rowbuf = smem_raw + head + (size_t)warp * p.rows_cap * p.chunk_bytes;
     float *wbuf = reinterpret_cast<float *>(smem_raw + head + (size_t)kWarps * p.rows_cap * p.chunk_bytes) + warp * p.rows_cap;   // BILINEAR: weight per slot
@@ -131,18 +135,27 @@ aggregate_views_kernel(const __grid_constant__ AggParams p) {
     //                 Fewer instructions per voxel, but the voxels in flight span T times more columns: it pays on fine
     //                 grids, where a pixel's row is gathered ~20 times and the L2 window is lost anyway (cfg 4: 2.08 ->
     //                 1.89 ms), not where the window just fits (cfg 2: 0.286 -> 0.313 ms); profiles/r02_kernels.md.
+    //   CTA columns   slabs of 8 slices; a CTA takes one column and its eight warps one voxel each, after culling the
+    //                 views TOGETHER (each warp tests 32 views, one CTA barrier): the instruction saving of column units
+    //                 with the voxels in flight as close together as with voxel units.
     const int warps_total = gridDim.x * kWarps;
     const int columns = p.g.nx * p.g.ny;
     const int nslabs = p.sweep.nfull + (p.sweep.nfull * p.sweep.T < p.g.nz ? 1 : 0);
     const float inv_columns = 1.0f / (float)columns;
-    // Every warp takes the same number of whole columns, round-robin; the columns left over after the last full round
-    // are dealt out voxel by voxel (one-voxel units), so that no warp runs a whole column longer than the others.
     const int total_columns = columns * nslabs;
-    const int full_columns = p.cull ? (total_columns / warps_total) * warps_total : 0;
+    // column units: every warp takes the same number of whole columns, round-robin; the columns left over after the last
+    // full round are dealt out voxel by voxel (one-voxel units), so that no warp runs a whole column longer than the others
+    const int full_columns = (p.cull == 1) ? (total_columns / warps_total) * warps_total : 0;
     const int total_units = full_columns + (total_columns - full_columns) * p.sweep.T;
-    for (int u = blockIdx.x * kWarps + warp; u < total_units; u += warps_total) {
+    // CTA columns: the CTA walks the columns (slabs of kWarps slices), warp w takes the column's w-th voxel
+    const bool cta_mode = p.cull == 2;
+    const int u_first = cta_mode ? (int)blockIdx.x : (int)blockIdx.x * kWarps + warp;
+    const int u_step = cta_mode ? (int)gridDim.x : warps_total;
+    const int u_total = cta_mode ? total_columns : total_units;
+    int round_robin = 0;   // CTA columns: which of the two shared survivor buffers this column uses
+    for (int u = u_first; u < u_total; u += u_step, round_robin ^= 1) {
         int col = u, zfirst = 0, zcount = p.sweep.T;
-        if (u >= full_columns) {
+        if (!cta_mode && u >= full_columns) {
             fast_divmod(u - full_columns, p.sweep.T, p.sweep.inv_T, col, zfirst);
             col += full_columns;
             zcount = 1;
@@ -150,31 +163,55 @@ aggregate_views_kernel(const __grid_constant__ AggParams p) {
         int slab, xy, vx, vy;
         fast_divmod(col, columns, inv_columns, slab, xy);
         fast_divmod(xy, p.g.ny, p.sweep.inv_ny, vx, vy);
-        const int z0 = slab * p.sweep.T + zfirst;
-        const int nzu = min(zcount, p.g.nz - z0);     // <= 0: a one-voxel unit beyond the last (thinner) slab
-        if (nzu <= 0) continue;
+        int z0 = slab * p.sweep.T + zfirst;
+        int nzu = min(zcount, p.g.nz - z0);     // <= 0: a one-voxel unit beyond the last (thinner) slab
+        if (!cta_mode && nzu <= 0) continue;
         const float wx = world_coord(vx + p.g.x0, p.g.vs, p.g.ox);
         const float wy = world_coord(vy + p.g.y0, p.g.vs, p.g.oy);
         const float rho = 0.5f * (float)(nzu - 1) * p.g.vs;                          // half the column's length
         const float wzc = ((float)(z0 + p.g.z0) + 0.5f * (float)(nzu - 1)) * p.g.vs + p.g.oz;   // its centre (cull only)
+        // lane <-> view: may this view see any voxel of the column?  (conservative; see above)
+        auto column_may_be_seen = [&](int view) -> bool {
+            if (view >= p.V) return false;
+            const float *P = sP + view;
+            const float cx = row_dot4(P[0 * Vpad], P[1 * Vpad], P[2 * Vpad], P[3 * Vpad], wx, wy, wzc, 1.0f);
+            const float cy = row_dot4(P[4 * Vpad], P[5 * Vpad], P[6 * Vpad], P[7 * Vpad], wx, wy, wzc, 1.0f);
+            const float cz = row_dot4(P[8 * Vpad], P[9 * Vpad], P[10 * Vpad], P[11 * Vpad], wx, wy, wzc, 1.0f);
+            const float *Q = sCull + view;
+            const float slack = 1.0e-3f * (fabsf(cz) + rho * Q[4 * Vpad]);      // rounding of the fp32 chains: ~1e-6
+            return (cz + rho * Q[4 * Vpad] >= -slack) && (cx + 0.5f * cz + rho * Q[0 * Vpad] >= -slack) &&
+                   (fW * cz - cx + rho * Q[1 * Vpad] >= -slack) && (cy + 0.5f * cz + rho * Q[2 * Vpad] >= -slack) &&
+                   (fH * cz - cy + rho * Q[3 * Vpad] >= -slack);
+        };
         int ncand = p.cull ? 0 : p.V;
-        for (int v0 = 0; v0 < p.V && p.cull; v0 += 32) {
-            const int view = v0 + lane;
-            bool maybe = false;
-            if (view < p.V) {
-                const float *P = sP + view;
-                const float cx = row_dot4(P[0 * Vpad], P[1 * Vpad], P[2 * Vpad], P[3 * Vpad], wx, wy, wzc, 1.0f);
-                const float cy = row_dot4(P[4 * Vpad], P[5 * Vpad], P[6 * Vpad], P[7 * Vpad], wx, wy, wzc, 1.0f);
-                const float cz = row_dot4(P[8 * Vpad], P[9 * Vpad], P[10 * Vpad], P[11 * Vpad], wx, wy, wzc, 1.0f);
-                const float *Q = sCull + view;
-                const float slack = 1.0e-3f * (fabsf(cz) + rho * Q[4 * Vpad]);      // rounding of the fp32 chains: ~1e-6
-                maybe = (cz + rho * Q[4 * Vpad] >= -slack) && (cx + 0.5f * cz + rho * Q[0 * Vpad] >= -slack) &&
-                        (fW * cz - cx + rho * Q[1 * Vpad] >= -slack) && (cy + 0.5f * cz + rho * Q[2 * Vpad] >= -slack) &&
-                        (fH * cz - cy + rho * Q[3 * Vpad] >= -slack);
+        if (cta_mode) {
+            // the warps share the cull: warp w tests views 32 w .. 32 w + 31 (+ 256 ...) and leaves the survivors of its
+            // round in shared memory; after ONE CTA barrier every warp strings the rounds together into its own list.
+            // Two buffers: a warp that is ahead writes the next column's survivors while a slower one still reads this
+            // column's -- the barrier of the next column is what separates columns two apart.
+            uint16_t *cand_r = sCandR + round_robin * cull_rounds * 32;
+            int *cnt_r = sCnt + round_robin * cull_rounds;
+            for (int r = warp; r < cull_rounds; r += kWarps) {
+                const bool maybe = column_may_be_seen(r * 32 + lane);
+                const unsigned mb = __ballot_sync(0xffffffffu, maybe);
+                if (maybe) cand_r[r * 32 + __popc(mb & ((1u << lane) - 1u))] = (uint16_t)(r * 32 + lane);
+                if (lane == 0) cnt_r[r] = __popc(mb);
             }
-            const unsigned mb = __ballot_sync(0xffffffffu, maybe);
-            if (maybe) sCand[ncand + __popc(mb & ((1u << lane) - 1u))] = (uint16_t)view;
-            ncand += __popc(mb);
+            __syncthreads();
+            for (int r = 0; r < cull_rounds; ++r) {
+                const int c = cnt_r[r];
+                if (lane < c) sCand[ncand + lane] = cand_r[r * 32 + lane];
+                ncand += c;
+            }
+            z0 += warp;                            // this warp's voxel of the column
+            nzu = (warp < nzu) ? 1 : 0;
+        } else if (p.cull) {
+            for (int v0 = 0; v0 < p.V; v0 += 32) {
+                const bool maybe = column_may_be_seen(v0 + lane);
+                const unsigned mb = __ballot_sync(0xffffffffu, maybe);
+                if (maybe) sCand[ncand + __popc(mb & ((1u << lane) - 1u))] = (uint16_t)(v0 + lane);
+                ncand += __popc(mb);
+            }
         }
         __syncwarp();
       for (int zi = 0; zi < nzu; ++zi) {
@@ -473,7 +510,8 @@ cudaError_t run_aggregate_views(const GridDev &g, const cnrma_features &f, int v
     // column units + view culling where every pixel row is gathered many times over (see the kernel): about a quarter of
     // the views see a voxel, so a row is gathered ~nvox / (4 H W) times
     p.cull = (double)p.nvox >= 32.0 * f.height * f.width;
-    if (tuning().agg_cull >= 0) p.cull = tuning().agg_cull;   // CNRMA_AGG_CULL
+    if (tuning().agg_cull >= 0) p.cull = tuning().agg_cull;   // CNRMA_AGG_CULL = 0 | 1 | 2
+    if (p.cull == 2) p.sweep = make_sweep(g.nx, g.ny, g.nz, kAggThreads / kWarp);   // CTA columns: one slice per warp
     return run_aggregate(p, f.dtype, max_chunk_bytes, stream);
 }
 
