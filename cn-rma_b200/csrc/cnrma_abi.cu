@@ -16,6 +16,7 @@ static Tuning read_tuning() {
     t.agg_slab = num("CNRMA_AGG_SLAB");
     t.agg_tile = num("CNRMA_AGG_TILE");
     if (const char *e = std::getenv("CNRMA_AGG_CULL")) t.agg_cull = std::atoi(e);
+    if (const char *e = std::getenv("CNRMA_AGG_PIPE")) t.agg_pipe = std::atoi(e);
     t.agg_chunk_bytes = num("CNRMA_AGG_CHUNK_BYTES");
     t.agg_warp_buffer = num("CNRMA_AGG_WARP_BUFFER");
     t.agg_list_views = num("CNRMA_AGG_LIST_VIEWS");

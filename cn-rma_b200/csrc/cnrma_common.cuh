@@ -28,6 +28,7 @@ struct Tuning {
     int agg_slab = 0;           // CNRMA_AGG_SLAB: slab thickness of the Stage A sweep, 0 automatic
     int agg_tile = 0;           // CNRMA_AGG_TILE: (x, y) tile edge inside a slab, 0 none
     int agg_cull = -1;          // CNRMA_AGG_CULL: -1 automatic, 0 voxel units, 1 column units with view culling, 2 CTA columns
+    int agg_pipe = -1;          // CNRMA_AGG_PIPE: 1 selects the software-pipelined form of the TMA kernel (opt-in)
     int agg_chunk_bytes = 0;    // CNRMA_AGG_CHUNK_BYTES
     int agg_warp_buffer = 0;    // CNRMA_AGG_WARP_BUFFER
     int agg_list_views = 0;     // CNRMA_AGG_LIST_VIEWS

@@ -58,12 +58,17 @@ def test_golden_indices_and_masks_bit_exact(cn, golden):
 
 
 @pytest.mark.parametrize("kernel,slab", [("default", None), ("tma", None), ("list", None), ("tma", "1"), ("list", "3"),
-                                         ("tma+cull", None), ("tma+cull", "3"), ("tma-cull", None), ("tma*cull", None)])
+                                         ("tma+cull", None), ("tma+cull", "3"), ("tma-cull", None), ("tma*cull", None),
+                                         ("tma-pipe", None), ("tma-pipe", "2")])
 @pytest.mark.parametrize("channels_last", [True, False])
 def test_golden_stage_a_bit_exact(cn, golden, channels_last, kernel, slab, monkeypatch):
     """The reference's sums / counts / means through both Stage A kernels, several sweep orders, and both work-unit
     granularities of the TMA kernel (one voxel / a column of the slab with view culling per warp / per CTA)."""
-    if kernel.startswith("tma") and len(kernel) > 3:
+    if kernel == "tma-pipe":                       # voxel units, software-pipelined form (opt-in)
+        monkeypatch.setenv("CNRMA_AGG_CULL", "0")
+        monkeypatch.setenv("CNRMA_AGG_PIPE", "1")
+        kernel = "tma"
+    elif kernel.startswith("tma") and len(kernel) > 3:
         monkeypatch.setenv("CNRMA_AGG_CULL", {"+": "1", "-": "0", "*": "2"}[kernel[3]])
         kernel = "tma"
     if kernel != "default":

@@ -59,15 +59,17 @@ def test_random_scene(seed):
 
 
 @pytest.mark.parametrize("seed", range(int(os.environ.get("CNRMA_RANDOM_SEEDS", "24"))))
-@pytest.mark.parametrize("slab", [None, "1", "5", "cta"])
+@pytest.mark.parametrize("slab", [None, "1", "5", "cta", "pipe"])
 def test_random_scene_stage_a_with_view_culling(seed, slab, monkeypatch):
     """The TMA gather kernel in column units: a conservative per-column cull of the views, then the exact projection over
     the survivors.  Random cameras (outside the grid, looking away, singular-ish intrinsics) and column lengths: a view
     that is culled wrongly would change a count or a sum."""
     import cnrma_b200 as cn
     monkeypatch.setenv("CNRMA_AGG_KERNEL", "tma")
-    monkeypatch.setenv("CNRMA_AGG_CULL", "2" if slab == "cta" else "1")     # CTA columns / per-warp columns
-    if slab not in (None, "cta"):
+    monkeypatch.setenv("CNRMA_AGG_CULL", {"cta": "2", "pipe": "0"}.get(slab, "1"))   # CTA / no cull (pipelined) / per warp
+    if slab == "pipe":
+        monkeypatch.setenv("CNRMA_AGG_PIPE", "1")
+    if slab not in (None, "cta", "pipe"):
         monkeypatch.setenv("CNRMA_AGG_SLAB", slab)
     s = _random_scene(np.random.default_rng(3000 + seed))
     f = torch.from_numpy(s["feats"]).cuda().unsqueeze(1).permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
