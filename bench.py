@@ -732,26 +732,36 @@ def run_e2e(args, cn, scenes, dev, world, max_rows, handoff_rows=None):
     """The same step through the stateful host mirror of the reference detector's aggregation methods
     (cn.RayMarchingAggregator) with HOST buffers: every step copies its scene's inputs from pinned host memory to the
     device and its results (volume, count, points) back to pinned host memory.  Three streams (copy-in, compute,
-    copy-out); device inputs and host outputs are double-buffered so that the next scene's upload and the previous
-    scene's download overlap with the kernels and with each other; timed with CUDA events from the first upload to the
-    last download, max over ranks.  With `handoff_rows` the lift is fused with the detector's point-cloud hand-off
+    copy-out); device inputs are double-buffered so that the next scene's upload and the previous scene's download overlap
+    with the kernels and with each other; timed with CUDA events from the first upload to the last download, max over
+    ranks.  With `handoff_rows` the lift is fused with the detector's point-cloud hand-off
     (rm.py:339-407): only the kept rows are produced and downloaded."""
     import torch
     import torch.distributed as dist
     sc = scenes[0]["sc"]
     V, C, H, W = sc.views, sc.channels, sc.height, sc.width
     nx, ny, nz = sc.voxel_dim
-    hosts = []
-    for s_ in scenes[:2 if world < 4 else 1]:               # host scenes alternate (pinned, like a dataloader's)
-        f = s_["feats"]
-        h_feats = torch.empty(f.permute(0, 1, 3, 4, 2).shape, dtype=f.dtype).pin_memory()
-        h_feats.copy_(f.permute(0, 1, 3, 4, 2))
-        hosts.append(dict(feats=h_feats, proj=s_["proj_host"].pin_memory(), tsdf=s_["tsdf"].cpu().pin_memory()))
-    # one pinned result slot: the downloads of consecutive steps are ordered on the copy-out stream, and nobody reads
-    # the host copy in between (8 ranks x 8 GB of pinned rows is what the host can spare)
-    outs = [dict(vol=torch.empty((1, nx, ny, nz, C), dtype=torch.float32).pin_memory(),
-                 cnt=torch.empty((1, 1, nx, ny, nz), dtype=torch.int32).pin_memory(),
-                 pts=torch.empty((handoff_rows or int(max_rows) + 4096, 3 + C), dtype=torch.float32).pin_memory())]
+    hosts, outs, ok = [], [], 1
+    try:
+        for s_ in scenes[:2 if world < 4 else 1]:               # host scenes alternate (pinned, like a dataloader's)
+            f = s_["feats"]
+            h_feats = torch.empty(f.permute(0, 1, 3, 4, 2).shape, dtype=f.dtype).pin_memory()
+            h_feats.copy_(f.permute(0, 1, 3, 4, 2))
+            hosts.append(dict(feats=h_feats, proj=s_["proj_host"].pin_memory(), tsdf=s_["tsdf"].cpu().pin_memory()))
+        # one pinned result slot: the downloads of consecutive steps are ordered on the copy-out stream, and nobody reads
+        # the host copy in between (8 ranks x 8 GB of pinned rows is what the host can spare)
+        outs = [dict(vol=torch.empty((1, nx, ny, nz, C), dtype=torch.float32).pin_memory(),
+                     cnt=torch.empty((1, 1, nx, ny, nz), dtype=torch.int32).pin_memory(),
+                     pts=torch.empty((handoff_rows or int(max_rows) + 4096, 3 + C), dtype=torch.float32).pin_memory())]
+    except RuntimeError:
+        ok = 0
+    if world > 1:                                               # every rank or none: the leg has collectives
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = int(flag.item())
+    if not ok:
+        return {"value": None, "unit": "voxel*views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "error": "the host could not pin the buffers of the end-to-end leg on every rank"}
     ag = cn.RayMarchingAggregator(sc.voxel_size, sc.voxel_dim, origin=sc.origin.tolist(), backbone2d_stride=sc.stride,
                                   neus_threshold=args.threshold)
     s_in, s_cmp, s_out = (torch.cuda.Stream(device=dev) for _ in range(3))

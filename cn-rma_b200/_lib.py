@@ -10,7 +10,8 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "libcnrma_b200.so")
+# CNRMA_LIB: load another build of the library (A/B runs of compile-time variants; see profiles/); default: the in-tree one
+LIB_PATH = os.environ.get("CNRMA_LIB") or os.path.join(_HERE, "libcnrma_b200.so")
 SOURCES = ["cnrma_abi.cu", "cnrma_stage_a.cu", "cnrma_stage_a_list.cu", "cnrma_stage_a_bilinear.cu", "cnrma_tsdf_head.cu", "cnrma_stage_b.cu", "cnrma_backward.cu",
            "cnrma_handoff.cu", "cnrma_fusion.cu", "cnrma_exchange.cu"]
 HEADERS = ["cnrma_common.cuh", "cnrma_internal.cuh", os.path.join("..", "..", "include", "cnrma_b200.h")]

@@ -218,6 +218,10 @@ __global__ void __launch_bounds__(kListThreads) aggregate_views_list_kernel(cons
 // whose bf16 halves are widened one by one -- at 57 % of the issue slots: instruction-bound with the rest lost to L2
 // latency (profiles/r02_kernels.md).
 constexpr int kLongVoxels = 8;     // voxels per unit
+#ifndef CNRMA_LONG_UNROLL
+#define CNRMA_LONG_UNROLL 4
+#endif
+constexpr int kLongUnroll = CNRMA_LONG_UNROLL;   // rows in flight per lane group in phase 2
 constexpr int kLongStep = 4;       // views per phase-1 step (lane = sub * 8 + voxel)
 
 template <int G, int VPL, typename T, bool UNIFORM>
@@ -331,10 +335,10 @@ __global__ void __launch_bounds__(kListThreads) aggregate_views_long_kernel(cons
                 int nmax = nn;   // longest list among the groups of this warp
 #pragma unroll
                 for (int o = 16; o >= G; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
-                for (int k = 0; k < nmax; k += kListUnroll) {
-                    uint4 raw[kListUnroll][VPL];
+                for (int k = 0; k < nmax; k += kLongUnroll) {
+                    uint4 raw[kLongUnroll][VPL];
 #pragma unroll
-                    for (int uu = 0; uu < kListUnroll; ++uu) {
+                    for (int uu = 0; uu < kLongUnroll; ++uu) {
                         if (k + uu < nn) {
                             const uint32_t e = jl[k + uu];
                             const unsigned char *src =
@@ -346,7 +350,7 @@ __global__ void __launch_bounds__(kListThreads) aggregate_views_long_kernel(cons
                         }
                     }
 #pragma unroll
-                    for (int uu = 0; uu < kListUnroll; ++uu) {
+                    for (int uu = 0; uu < kLongUnroll; ++uu) {
                         if (k + uu < nn) {
 #pragma unroll
                             for (int q = 0; q < VPL; ++q) {

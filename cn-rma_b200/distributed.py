@@ -471,14 +471,14 @@ class ViewExchange:
 
         with torch.cuda.device(dev):
             stamp(main, "start")
-            self.hdl.barrier(channel=0)                       # every rank's views are in its symmetric buffer
-            start = torch.cuda.Event()
-            start.record(main)
-            stamp(main, "barrier")
-            self.side.wait_event(start)
+            entered = torch.cuda.Event()
+            entered.record(main)
+            self.side.wait_event(entered)
             arrived = []
             with torch.cuda.stream(self.side):
                 if order:
+                    # which rows this box needs is a matter of cameras and geometry only: the marks run BEFORE the
+                    # barrier, beside whatever the peers are still doing
                     self._bm[: len(xparts) + 1].zero_()
                     self._work.zero_()
                     box = _lib.make_box(lo, dim)              # the rows every part needs from the remote views
@@ -488,6 +488,12 @@ class ViewExchange:
                                                        C.c_void_p(self._bm[1, a].data_ptr()), len(xparts),
                                                        self.V * self.words, F._stream(dev)), "cnrma_mark_rows")
                     stamp(self.side, "marks")
+            self.hdl.barrier(channel=0)                       # every rank's views are in its symmetric buffer
+            start = torch.cuda.Event()
+            start.record(main)
+            stamp(main, "barrier")
+            self.side.wait_event(start)
+            with torch.cuda.stream(self.side):
                 for k in range(len(xparts) if order else 0):
                     _lib.check(lib.cnrma_pull_rows(C.c_void_p(self._bm[k + 1].data_ptr()), C.c_void_p(done.data_ptr()),
                                                    self.V, self.H, self.W, self.row_bytes, self._owner_ptrs,
