@@ -311,7 +311,8 @@ def bench_config(args, sc, world):
                    "inputs (%.0f MB features/scene, %d scenes rotated) may FIT the 126 MB L2 and no flush is done: this "
                    "configuration's numbers include L2 reuse across steps") % (feat_mb, args.scenes),
             "parallelism": f"scene-dp{world}", "threshold": args.threshold,
-            "scenes": f"{args.scenes} seeded scenes per rank, rotated step by step (cameras and room differ: M varies)"}
+            "scenes": f"{args.scenes} seeded scenes (the same on every rank, rank-dependent start), rotated step by step "
+                      "(cameras and room differ: M varies)"}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -353,7 +354,9 @@ def main():
     override = scene_override(args.config)
     scenes = []
     for i in range(args.scenes):
-        sc = cn.synthetic.make_scene(args.config, seed=rank * args.scenes + i, with_features=False, **override)
+        # the same seeds on every rank (weak scaling: identical work per rank), visited from a rank-dependent start, so
+        # that at any step the ranks are on different scenes
+        sc = cn.synthetic.make_scene(args.config, seed=i, with_features=False, **override)
         feats = cn.synthetic.device_features(sc, dev, channels_last=True)           # [V,1,C,H,W] logical
         if sc.meta.get("dtype") == "bf16":
             feats = feats.to(torch.bfloat16)
@@ -370,7 +373,7 @@ def main():
     F.set_phase_hook(lambda label: marks["ev"][2].record() if marks.get("ev") else None)
 
     def step(k, ev=None):
-        s_ = scenes[k % len(scenes)]
+        s_ = scenes[(k + rank) % len(scenes)]
         marks["ev"] = ev
         if ev:
             ev[0].record()
