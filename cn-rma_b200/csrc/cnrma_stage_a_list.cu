@@ -44,7 +44,13 @@ struct ListParams {
 
 constexpr int kListThreads = 256;
 constexpr int kListUnroll = 4;
-constexpr int kLongListCap = 161;   // entries per voxel list of the long-list kernel (odd); longer lists go out in segments
+#ifndef CNRMA_LONG_CAP
+#define CNRMA_LONG_CAP 161
+#endif
+#ifndef CNRMA_LONG_MINB
+#define CNRMA_LONG_MINB 3   // 3 CTAs of 80 registers per SM (4 x 64 registers: 21.9 ms on cfg 5 against 19.1; 6 or 8 rows in flight at 105-116 registers: 21.3 / 20.8)
+#endif
+constexpr int kLongListCap = CNRMA_LONG_CAP;   // entries per voxel list of the long-list kernel (odd); longer lists go out in segments
 
 template <int G, int VPL, typename T, bool UNIFORM>
 __global__ void __launch_bounds__(kListThreads) aggregate_views_list_kernel(const __grid_constant__ ListParams p) {
@@ -225,7 +231,7 @@ constexpr int kLongUnroll = CNRMA_LONG_UNROLL;   // rows in flight per lane grou
 constexpr int kLongStep = 4;       // views per phase-1 step (lane = sub * 8 + voxel)
 
 template <int G, int VPL, typename T, bool UNIFORM>
-__global__ void __launch_bounds__(kListThreads) aggregate_views_long_kernel(const __grid_constant__ ListParams p) {
+__global__ void __launch_bounds__(kListThreads, (VPL == 1) ? CNRMA_LONG_MINB : 1) aggregate_views_long_kernel(const __grid_constant__ ListParams p) {
     using V16 = Vec16<T>;
     constexpr int E = V16::kElems;
     constexpr int kWarps = kListThreads / kWarp;
