@@ -679,6 +679,16 @@ def view_sharded_suite(cn, dev, rank, world, config="cfg4", steps=20, warmup=3, 
     box_ms = timed(lambda: cn.aggregate_views(proj, full, *args, box=(blo, bdim)), n=10)
     out["exchange_phases_ms"] = prof
     out["box_gather_alone_ms"] = box_ms
+    # the ray-driven point form shards by view without any exchange of rows: every rank marches its own views and scales
+    # its rows by the GLOBAL mean weight (two scalars all-reduced); rank order == view order
+    tsdf = torch.from_numpy(sc.tsdf).to(dev)[None, None]
+    proj_host = torch.from_numpy(sc.projections).unsqueeze(1)
+    thr = 0.05
+    pts_single = timed(lambda: cn.rma_points(proj_host, full, tsdf, *args, grids=sc.grids, threshold=thr), n=10)
+    pts_sharded = timed(lambda: D.rma_points_sharded(proj_host[lo:hi], feats, tsdf, *args, grids=sc.grids, threshold=thr), n=10)
+    out["points_sharded"] = {"single_gpu_ms": pts_single, "ms": pts_sharded, "speedup_vs_1gpu": pts_single / pts_sharded,
+                             "what": "rma_points (march + fill of [M,3+C] rows) with the views sharded; one all-reduce of "
+                                     "(sum of weights, M); rows stay on the rank that made them"}
     out["volume_bytes"] = vol_bytes
     out["feature_bytes"] = feat_bytes
     best = min(out["modes"].items(), key=lambda kv: kv[1]["ms"]) if out["modes"] else None

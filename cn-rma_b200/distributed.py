@@ -246,11 +246,15 @@ def rma_points_sharded(projections, features, tsdf, voxel_dim, voxel_size, origi
     == view order, so concatenating the ranks' outputs reproduces the single-GPU row order."""
     _rank, world = _world(group)
 
-    def global_mean(weight_sum, rows, device):
-        tot = torch.tensor([weight_sum, float(rows)], dtype=torch.float64, device=device)
+    def global_mean(result_block):
+        """(sum of weights, M) of this rank's views, read from the march's result block on the device, all-reduced; no
+        host round trip, so the fill is queued right behind the collective."""
+        tot = torch.cat((result_block[8:16].view(torch.float64), result_block[0:8].view(torch.int64).to(torch.float64)))
         if world > 1:
             dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
         return (tot[0] / tot[1]).to(torch.float32).reshape(1)
+
+    global_mean.on_device = True
 
     return F.rma_points(projections, features, tsdf, voxel_dim, voxel_size, origin, stride, grids=grids, mode=mode,
                         threshold=threshold, depth_points=depth_points, normalize=True, mean_hook=global_mean)

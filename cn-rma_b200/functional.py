@@ -609,19 +609,26 @@ def _march_and_fill(fs, b, m, grid, normalize, mean_hook, key, desc=None):
     desc = desc if desc is not None else fs.descriptor(b)
     hint = _hint_rows(key)
     rows = None
-    if hint and mean_hook is None:
-        rows = _fill(fs, b, m, grid, -1, normalize, None, desc, capacity=hint)
+    mean_t = None
+    on_device = mean_hook is not None and normalize and getattr(mean_hook, "on_device", False)
+    if on_device:
+        # the divisor is computed from the march's result block IN DEVICE MEMORY (e.g. all-reduced over the ranks of a
+        # view-sharded scene): nothing waits for the host, the fill can still be queued before M is known
+        mean_t = mean_hook(m.result)
+    speculative = bool(hint) and (mean_hook is None or on_device or not normalize)
+    if speculative:
+        rows = _fill(fs, b, m, grid, -1, normalize, mean_t, desc, capacity=hint)
     res = _read_result(m)
     n = int(res.rows)
     missed = rows is not None and n > rows.shape[0]
-    mean_t = None
     if rows is None or missed:
-        mean_t = mean_hook(res.weight_sum, res.rows, device) if (mean_hook and normalize) else None
+        if mean_t is None and mean_hook and normalize:
+            mean_t = mean_hook(res.weight_sum, res.rows, device)
         rows = _fill(fs, b, m, grid, n, normalize, mean_t, desc)
     _note_rows(key, n)
     with _state_lock:
         _fill_counters["calls"] += 1
-        _fill_counters["speculative"] += 1 if hint and mean_hook is None else 0
+        _fill_counters["speculative"] += 1 if speculative else 0
         _fill_counters["misses"] += 1 if missed else 0
     return rows[:n], res, mean_t
 
@@ -645,7 +652,10 @@ def rma_points(projections, features, tsdf, voxel_dim, voxel_size, origin, strid
     Returns a list over the batch of [M,3+C] tensors (rows [x,y,z, feat*w/mean(w)] in (view, v, u, step)
     order); with normalize=False the un-normalised [M,4+C] rows ([x,y,z,w,feat]) the per-view function
     returns.  A batch element with no kept sample yields an empty [0, .] tensor (the reference raises).
-    `mean_hook(weight_sum, rows, device) -> float32 CUDA tensor [1]` overrides the divisor of rm.py:303."""
+    `mean_hook(weight_sum, rows, device) -> float32 CUDA tensor [1]` overrides the divisor of rm.py:303; a hook with the
+    attribute `on_device = True` is called as `mean_hook(result_block)` instead, with the march's 32-byte result block
+    (cnrma_rma_result: rows int64 at byte 0, weight_sum double at byte 8) as a uint8 CUDA tensor, and must not
+    synchronise -- the fill is then queued without waiting for the host (distributed.rma_points_sharded)."""
     _check_mode(mode, threshold, depth_points)
     view_list = [features] if isinstance(features, torch.Tensor) else _as_view_list(features)
     with_grad = _needs_grad(view_list)
