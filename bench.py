@@ -229,7 +229,18 @@ def run_reference_arm(args):
         ref_runner.reference_pass(sc, probe, probe_ids, args.threshold, threads)          # import, page in
         a, b, _ = ref_runner.reference_pass(sc, probe, probe_ids, args.threshold, threads)
         per_view = max((a + b) / 2.0, 1e-3)
-        n_views = args.cpu_views or int(max(1, min(sc.views, budget_s / max(passes, 1) / per_view)))
+        target = budget_s / max(passes, 1)
+        n_views = args.cpu_views or int(max(1, min(sc.views, target / per_view)))
+        # the reference's cost per view GROWS with the number of views (rm.py:289-293 re-copies the growing point cloud at
+        # every view), so the two-view probe flatters it: calibrate on the chosen sample and shrink it until a pass fits
+        for _ in range(2):
+            if args.cpu_views or n_views <= 1:
+                break
+            ids = sample_view_ids(sc.views, n_views)
+            a, b, _ = ref_runner.reference_pass(sc, cpu_features(sc, ids), ids, args.threshold, threads)
+            if a + b <= 1.2 * target:
+                break
+            n_views = max(1, int(n_views * (target / (a + b)) ** 0.75))
         ids = sample_view_ids(sc.views, n_views)
         feats = cpu_features(sc, ids)
         step = lambda: ref_runner.reference_pass(sc, feats, ids, args.threshold, threads)
