@@ -12,7 +12,7 @@ struct RmaWorkspace {
     int64_t rays;     // V*H*W
     int64_t blocks;   // ceil(rays / kRayThreads)
     int cap;          // (step, weight) records per ray
-    size_t off_counts, off_blk_rows, off_blk_wsum, off_blk_off, off_rec_w, off_rec_i, off_dist, off_sigmoid, total;
+    size_t off_counts, off_blk_rows, off_blk_wsum, off_blk_off, off_rec_w, off_rec_i, off_dist, off_sigmoid, off_cell, total;
 };
 
 // cnrma_stage_a.cu

@@ -44,6 +44,7 @@ RmaWorkspace rma_workspace(int views, int height, int width, int grids, int mode
     w.off_rec_i = o;    o = align256(o + sizeof(float) * (size_t)w.rays * (size_t)w.cap);
     w.off_dist = o;     o = align256(o + 2 * (size_t)nvox);   // two uint8 distance fields (ping-pong)
     w.off_sigmoid = o;  o = align256(o + sizeof(float) * (size_t)nvox);
+    w.off_cell = o;     o = align256(o + sizeof(uint2) * (size_t)nvox);   // {bits of s, clearance} per voxel
     w.total = o;
     return w;
 }
@@ -64,6 +65,7 @@ struct MarchParams {
     cnrma_rma_result *result;
     const uint8_t *dist;     // [nvox] Chebyshev distance (capped) to the nearest voxel of another sigmoid value
     const float *sig;        // [nvox] sigmoid(-tsdf), written by tsdf_prepare_kernel
+    const uint2 *cell;       // [nvox] {bits of sig, dist}: what a skipping march reads per sample, in one 8-byte load
 };
 
 __device__ __forceinline__ float sigmoid_neg(float tv) {
@@ -166,8 +168,10 @@ __global__ void __launch_bounds__(256) dist_boundary_kernel(GridDev g, const flo
 }
 
 // Separable L-infinity distance transform: out(v) = min over |d| <= cap along `axis` of max(|d|, in(v + d)).
+// The last pass also writes the march's combined table when `cell` is given.
 __global__ void __launch_bounds__(256) dist_pass_kernel(GridDev g, int axis, const uint8_t *__restrict__ in,
-                                                        uint8_t *__restrict__ out) {
+                                                        uint8_t *__restrict__ out, const float *__restrict__ sig = nullptr,
+                                                        uint2 *__restrict__ cell = nullptr) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= g.nx * g.ny * g.nz) return;
     const int z = v % g.nz, xy = v / g.nz, y = xy % g.ny, x = xy / g.ny;
@@ -180,6 +184,7 @@ __global__ void __launch_bounds__(256) dist_pass_kernel(GridDev g, int axis, con
         if (pos + d < n) best = min(best, max(d, (int)in[v + d * stride]));
     }
     out[v] = (uint8_t)best;
+    if (cell != nullptr) cell[v] = make_uint2(__float_as_uint(sig[v]), (unsigned)best);
 }
 
 // Fused pre-pass for grids whose (y, z) plane fits shared memory: one CTA per x index tabulates s for its plane,
@@ -292,6 +297,8 @@ __device__ __forceinline__ void block_totals(int kept, double wsum, int32_t *blk
 // Consecutive samples that read the same TSDF value (same voxel, or neighbouring voxels of equal value such as
 // free space) have alpha == 0 exactly: the transmittance is unchanged and, for thr > 0, nothing is kept, so the
 // exp / divisions are only evaluated where the TSDF value changes.
+// SKIP: thr > 0 and the clearance table exists (the normal case); one 8-byte load per sample brings s and the clearance.
+template <bool SKIP>
 __global__ void __launch_bounds__(kRayThreads) march_neus_kernel(const __grid_constant__ MarchParams p) {
     const int64_t ray = (int64_t)blockIdx.x * kRayThreads + threadIdx.x;
     int kept = 0;
@@ -303,12 +310,12 @@ __global__ void __launch_bounds__(kRayThreads) march_neus_kernel(const __grid_co
         float o[3], d[3];
         ray_of_pixel(p.pinv + 16 * view, pix % p.W, pix / p.W, o, d);
         const VoxelMap vm = make_voxel_map(p.g);
-        const bool keep_zero = !(p.thr > 0.0f);   // thr <= 0 (or NaN): zero weights pass `w >= thr` too
+        const bool keep_zero = SKIP ? false : !(p.thr > 0.0f);   // thr <= 0 (or NaN): zero weights pass `w >= thr` too
 
         // samples the ray may jump per voxel of clearance: 1 / max_a |d_a * t_one / vs|
         const float step_max = fmaxf(fmaxf(fabsf(d[0]), fabsf(d[1])), fabsf(d[2])) * p.t_one / p.g.vs;
         const float inv_step = (step_max > 0.0f) ? 1.0f / step_max : 0.0f;
-        const bool can_skip = !keep_zero && p.dist != nullptr;
+        const bool can_skip = SKIP;
         const int n_steps = ray_is_finite(o, d) ? p.N : -1;   // non-finite rays keep nothing (see sample_voxel)
 
         float T = 1.0f;
@@ -324,11 +331,21 @@ __global__ void __launch_bounds__(kRayThreads) march_neus_kernel(const __grid_co
             float s_next = s_cur;   // i == N: last sample repeated (rm.py:758); same voxel -> same value
             if (i < p.N) {
                 vox_next = sample_voxel(p.g, vm, o, d, __fmul_rn((float)i, p.t_one));
-if (i == 0 || vox_next != vox_cur) s_next = (vox_next >= 0) ? __ldg(p.sig + vox_next) : s_out;
                 // the clearance is re-read at every sample: keeping it in a register while the voxel is unchanged was
                 // measured and is slower (cfg 2 march phase 0.350 -> 0.383 ms, cfg 1 0.244 -> 0.264 ms: the load hits L1 and
                 // the extra live register / select costs more than it saves)
-                k_cur = (can_skip && vox_next >= 0) ? (int)__ldg(p.dist + vox_next) : 0;
+                if (SKIP) {
+                    s_next = s_out;
+                    k_cur = 0;
+                    if (vox_next >= 0) {
+                        const uint2 c = __ldg(p.cell + vox_next);
+                        s_next = __uint_as_float(c.x);
+                        k_cur = (int)c.y;
+                    }
+                } else {
+                    if (i == 0 || vox_next != vox_cur) s_next = (vox_next >= 0) ? __ldg(p.sig + vox_next) : s_out;
+                    k_cur = 0;
+                }
                 // clearance k voxels -> the next floor((k - margin) / step) samples read the same value
                 if (k_cur > 0) skip_to = i + (int)(((float)k_cur - kSkipMargin) * inv_step);
             }
@@ -348,7 +365,7 @@ if (i == 0 || vox_next != vox_cur) s_next = (vox_next >= 0) ? __ldg(p.sig + vox_
                 }
                 T = __fmul_rn(T, __fsub_rn(1.0f, a));
                 // exact early exit: every later weight is <= T < thr
-                if (p.thr > 0.0f && T < p.thr) break;
+                if ((SKIP || p.thr > 0.0f) && T < p.thr) break;
             }
             // exact early exit: the grid is convex and the rounded sample ids are monotone along the ray, so once
             // left it is never re-entered, and samples outside are never kept
@@ -824,6 +841,7 @@ cudaError_t run_march(const GridDev &g, const float *pinv, int V, int H, int W, 
     p.result = result;
     p.dist = nullptr;
     p.sig = nullptr;
+    p.cell = nullptr;
     cudaError_t err = cudaSuccess;
     const int nvox = g.nx * g.ny * g.nz;
     const size_t slab_bytes = 2 * (size_t)g.ny * g.nz;
@@ -837,6 +855,7 @@ cudaError_t run_march(const GridDev &g, const float *pinv, int V, int H, int W, 
         float *sig = reinterpret_cast<float *>(base + ws.off_sigmoid);
         uint8_t *d0 = reinterpret_cast<uint8_t *>(base + ws.off_dist);
         uint8_t *d1 = d0 + nvox;
+        uint2 *cell = reinterpret_cast<uint2 *>(base + ws.off_cell);
         p.sig = sig;
         if (slab) {
             static thread_local int attr_dev = -1;
@@ -849,8 +868,9 @@ cudaError_t run_march(const GridDev &g, const float *pinv, int V, int H, int W, 
             }
             tsdf_prepare_slab_kernel<<<(unsigned)g.nx, kSlabThreads, slab_bytes, stream>>>(g, tsdf, sig, thr > 0.0f ? d0 : nullptr, result);
             if (thr > 0.0f) {
-                dist_pass_kernel<<<vb, 256, 0, stream>>>(g, 0, d0, d1);
+                dist_pass_kernel<<<vb, 256, 0, stream>>>(g, 0, d0, d1, sig, cell);
                 p.dist = d1;
+                p.cell = cell;
             }
         } else {
             tsdf_sigmoid_kernel<<<vb, 256, 0, stream>>>(tsdf, nvox, sig);
@@ -858,8 +878,9 @@ cudaError_t run_march(const GridDev &g, const float *pinv, int V, int H, int W, 
                 dist_boundary_kernel<<<vb, 256, 0, stream>>>(g, sig, d0);
                 dist_pass_kernel<<<vb, 256, 0, stream>>>(g, 2, d0, d1);
                 dist_pass_kernel<<<vb, 256, 0, stream>>>(g, 1, d1, d0);
-                dist_pass_kernel<<<vb, 256, 0, stream>>>(g, 0, d0, d1);
+                dist_pass_kernel<<<vb, 256, 0, stream>>>(g, 0, d0, d1, sig, cell);
                 p.dist = d1;
+                p.cell = cell;
             }
         }
         err = cudaGetLastError();
@@ -867,8 +888,10 @@ cudaError_t run_march(const GridDev &g, const float *pinv, int V, int H, int W, 
     }
     if (mode == CNRMA_MARCH_DEPTH)
         march_depth_kernel<<<(unsigned)ws.blocks, kRayThreads, 0, stream>>>(p);
+    else if (p.cell != nullptr)
+        march_neus_kernel<true><<<(unsigned)ws.blocks, kRayThreads, 0, stream>>>(p);
     else
-        march_neus_kernel<<<(unsigned)ws.blocks, kRayThreads, 0, stream>>>(p);
+        march_neus_kernel<false><<<(unsigned)ws.blocks, kRayThreads, 0, stream>>>(p);
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
     scan_blocks_kernel<<<1, kScanThreads, 0, stream>>>(p.blk_rows, p.blk_wsum,
