@@ -23,6 +23,7 @@ static Tuning read_tuning() {
     if (const char *e = std::getenv("CNRMA_AGG_BWD_KERNEL")) t.agg_bwd_kernel = (e[0] == 'l') ? 1 : 0;
     t.bilinear_simple = std::getenv("CNRMA_BILINEAR_SIMPLE") != nullptr;
     t.march_unfused = std::getenv("CNRMA_MARCH_UNFUSED_PREPASS") != nullptr;
+    if (const char *e = std::getenv("CNRMA_MARCH_JUMP")) t.march_jump = std::atoi(e);
     if (const char *e = std::getenv("CNRMA_FILL_KERNEL")) t.fill_kernel = (e[0] == 'p') ? 1 : 0;
     t.fill_stage_half = num("CNRMA_FILL_STAGE_HALF");
     if (const char *e = std::getenv("CNRMA_FILL_SELECT_KERNEL")) t.fill_select_scalar = (e[0] == 's');

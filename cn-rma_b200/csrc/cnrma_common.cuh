@@ -35,6 +35,7 @@ struct Tuning {
     int agg_bwd_kernel = -1;    // CNRMA_AGG_BWD_KERNEL: -1 automatic, 0 bulk, 1 list
     int bilinear_simple = 0;    // CNRMA_BILINEAR_SIMPLE
     int march_unfused = 0;      // CNRMA_MARCH_UNFUSED_PREPASS
+    int march_jump = -1;        // CNRMA_MARCH_JUMP: -1 automatic, 0 clearance only, 1 clearance + position inside the voxel
     int fill_kernel = -1;       // CNRMA_FILL_KERNEL: -1 automatic, 0 tma, 1 packed
     int fill_stage_half = 0;    // CNRMA_FILL_STAGE_HALF
     int fill_select_scalar = 0; // CNRMA_FILL_SELECT_KERNEL=scalar

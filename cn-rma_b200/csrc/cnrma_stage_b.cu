@@ -88,23 +88,29 @@ struct VoxelMap {
 // One sample of a ray (rm.py:729-733): position -> rounded voxel id; returns the flat id or -1 outside the grid
 // (ix, iy, iz are the integer coordinates when inside).  Callers guarantee finite o, d (non-finite rays keep
 // nothing in the reference either: their ids convert to INT64_MIN and fail the bounds test).
+// `frac` (optional) receives the sample's offset from the centre of its voxel, in voxels, per axis (|frac| <= 0.5 up to
+// the 2^-22 relative error of q).
 __device__ __forceinline__ int sample_voxel(const GridDev &g, const VoxelMap &m, const float o[3], const float d[3],
-                                            float t, int &ix, int &iy, int &iz) {
+                                            float t, int &ix, int &iy, int &iz, float *frac = nullptr) {
     const float org[3] = {g.ox, g.oy, g.oz};
-    float rel[3], r[3];
+    float rel[3], r[3], q[3];
     bool ambiguous = false;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         const float p = __fadd_rn(o[a], __fmul_rn(d[a], t));
         rel[a] = m.zero_origin ? p : __fsub_rn(p, org[a]);
-        const float q = __fmul_rn(rel[a], m.inv_vs);
-        r[a] = rintf(q);
-        const float safe = __fmaf_rn(fabsf(q), -2.384185791015625e-07f, 0.5f);   // 0.5 - |q| * 2^-22
-        ambiguous = ambiguous || !(fabsf(__fsub_rn(q, r[a])) < safe);             // also true for huge q
+        q[a] = __fmul_rn(rel[a], m.inv_vs);
+        r[a] = rintf(q[a]);
+        const float safe = __fmaf_rn(fabsf(q[a]), -2.384185791015625e-07f, 0.5f);   // 0.5 - |q| * 2^-22
+        ambiguous = ambiguous || !(fabsf(__fsub_rn(q[a], r[a])) < safe);             // also true for huge q
     }
     if (ambiguous) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) r[a] = rintf(__fdiv_rn(rel[a], g.vs));
+    }
+    if (frac != nullptr) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) frac[a] = __fsub_rn(q[a], r[a]);
     }
     // integer-valued floats; __float2int_rn saturates, so far-away samples simply fail the unsigned range test
     ix = __float2int_rn(r[0]);
@@ -133,7 +139,11 @@ __device__ __forceinline__ bool ray_is_finite(const float o[3], const float d[3]
 // border, have D = 0).  A sample that rounds to voxel c sits within 0.5 voxel of its centre, so the next
 // n = floor((k - margin) / max_a |step_a|) samples stay within k + 0.5 - margin of the centre, round to voxels
 // inside that cube and read the same s: the march jumps over them.  ("step" is the per-sample advance in voxel
-// units; margin = 0.05 voxel dwarfs the ~1e-5 voxel fp32 error of o + d*t.)
+// units; margin = 0.05 voxel dwarfs the ~1e-5 voxel fp32 error of o + d*t.)  Where a sample advances well under a
+// voxel the march uses the sharper per-axis form: sample i + j sits at frac_a + j * step_a from the centre of the
+// voxel sample i rounded to (frac = its offset, |frac| <= 0.5), and reads the same s while
+// |frac_a + j * step_a| < k + 0.5 - margin on every axis -- which also covers k = 0: the further samples inside
+// one and the same voxel.  The march reads s and k with one 8-byte load from a combined table.
 constexpr int kDistCap = 15;
 constexpr float kSkipMargin = 0.05f;
 
@@ -298,8 +308,12 @@ __device__ __forceinline__ void block_totals(int kept, double wsum, int32_t *blk
 // free space) have alpha == 0 exactly: the transmittance is unchanged and, for thr > 0, nothing is kept, so the
 // exp / divisions are only evaluated where the TSDF value changes.
 // SKIP: thr > 0 and the clearance table exists (the normal case); one 8-byte load per sample brings s and the clearance.
-template <bool SKIP>
-__global__ void __launch_bounds__(kRayThreads) march_neus_kernel(const __grid_constant__ MarchParams p) {
+// FINE: the jump also uses where the sample sits inside its voxel (see the loop) -- three more multiply-adds per
+// sample that pay when a sample advances well under a voxel (cfg 2: 0.39 voxel per sample, march 0.316 -> 0.267 ms) and
+// cost a little when it advances more than one (the reference's 0.04 m grid: 1.25 voxels per sample, 0.465 -> 0.472 ms);
+// the launcher picks.  Registers capped at 40 (6 CTAs per SM): the FINE form would take 47, measured equal or slower.
+template <bool SKIP, bool FINE>
+__global__ void __launch_bounds__(kRayThreads, 6) march_neus_kernel(const __grid_constant__ MarchParams p) {
     const int64_t ray = (int64_t)blockIdx.x * kRayThreads + threadIdx.x;
     int kept = 0;
     double wsum = 0.0;
@@ -312,17 +326,25 @@ __global__ void __launch_bounds__(kRayThreads) march_neus_kernel(const __grid_co
         const VoxelMap vm = make_voxel_map(p.g);
         const bool keep_zero = SKIP ? false : !(p.thr > 0.0f);   // thr <= 0 (or NaN): zero weights pass `w >= thr` too
 
-        // samples the ray may jump per voxel of clearance: 1 / max_a |d_a * t_one / vs|
-        const float step_max = fmaxf(fmaxf(fabsf(d[0]), fabsf(d[1])), fabsf(d[2])) * p.t_one / p.g.vs;
-        const float inv_step = (step_max > 0.0f) ? 1.0f / step_max : 0.0f;
-        const bool can_skip = SKIP;
+        // FINE: samples per voxel of travel along each axis, signed: 1 / (d_a * t_one / vs).  (An axis the ray does not
+        // move along gets a huge finite value: it never limits the jump.)  Otherwise one figure for the fastest axis.
+        float inv_step[3];
+        if (FINE) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float step = d[a] * p.t_one / p.g.vs;
+                inv_step[a] = copysignf(1.0f / fmaxf(fabsf(step), 1e-6f), step);
+            }
+        } else {
+            const float step_max = fmaxf(fmaxf(fabsf(d[0]), fabsf(d[1])), fabsf(d[2])) * p.t_one / p.g.vs;
+            inv_step[0] = inv_step[1] = inv_step[2] = (step_max > 0.0f) ? 1.0f / step_max : 0.0f;
+        }
         const int n_steps = ray_is_finite(o, d) ? p.N : -1;   // non-finite rays keep nothing (see sample_voxel)
 
         float T = 1.0f;
         float s_cur = 0.0f;   // sigmoid(-tsdf) of the current sample (set at i == 0)
         const float s_out = sigmoid_neg(1.0f);   // samples outside the grid read tsdf = 1.0 (rm.py:744)
         int vox_cur = -1;
-        int k_cur = 0;        // clearance of the current voxel (0: none / skipping off)
         bool entered = false;
         int overflow = 0;
         for (int i = 0; i <= n_steps; ++i) {
@@ -330,24 +352,40 @@ __global__ void __launch_bounds__(kRayThreads) march_neus_kernel(const __grid_co
             int skip_to = -1;
             float s_next = s_cur;   // i == N: last sample repeated (rm.py:758); same voxel -> same value
             if (i < p.N) {
-                vox_next = sample_voxel(p.g, vm, o, d, __fmul_rn((float)i, p.t_one));
                 // the clearance is re-read at every sample: keeping it in a register while the voxel is unchanged was
                 // measured and is slower (cfg 2 march phase 0.350 -> 0.383 ms, cfg 1 0.244 -> 0.264 ms: the load hits L1 and
                 // the extra live register / select costs more than it saves)
-                if (SKIP) {
+                if (SKIP && FINE) {
+                    int ix, iy, iz;
+                    float frac[3];
+                    vox_next = sample_voxel(p.g, vm, o, d, __fmul_rn((float)i, p.t_one), ix, iy, iz, frac);
                     s_next = s_out;
-                    k_cur = 0;
                     if (vox_next >= 0) {
                         const uint2 c = __ldg(p.cell + vox_next);
                         s_next = __uint_as_float(c.x);
-                        k_cur = (int)c.y;
+                        // Clearance k: every voxel within k of this one (L-infinity) holds the same s.  Sample i + j sits at
+                        // frac_a + j * step_a from this voxel's centre; while that stays below k + 0.5 - margin on every axis
+                        // it rounds to a voxel inside that cube (for k = 0: to this very voxel) and reads the same s.
+                        const float room = (float)c.y + (0.5f - kSkipMargin);
+                        float n = __fmaf_rn(-frac[0], inv_step[0], room * fabsf(inv_step[0]));
+                        n = fminf(n, __fmaf_rn(-frac[1], inv_step[1], room * fabsf(inv_step[1])));
+                        n = fminf(n, __fmaf_rn(-frac[2], inv_step[2], room * fabsf(inv_step[2])));
+                        skip_to = i + (int)n;   // n < 1 (or negative): no jump
+                    }
+                } else if (SKIP) {
+                    vox_next = sample_voxel(p.g, vm, o, d, __fmul_rn((float)i, p.t_one));
+                    s_next = s_out;
+                    if (vox_next >= 0) {
+                        const uint2 c = __ldg(p.cell + vox_next);
+                        s_next = __uint_as_float(c.x);
+                        // wherever the sample sits in its voxel (at most 0.5 from the centre), the next
+                        // floor((k - margin) / step) samples stay inside the cube of clearance k
+                        if (c.y > 0) skip_to = i + (int)(((float)c.y - kSkipMargin) * inv_step[0]);
                     }
                 } else {
+                    vox_next = sample_voxel(p.g, vm, o, d, __fmul_rn((float)i, p.t_one));
                     if (i == 0 || vox_next != vox_cur) s_next = (vox_next >= 0) ? __ldg(p.sig + vox_next) : s_out;
-                    k_cur = 0;
                 }
-                // clearance k voxels -> the next floor((k - margin) / step) samples read the same value
-                if (k_cur > 0) skip_to = i + (int)(((float)k_cur - kSkipMargin) * inv_step);
             }
             if (i > 0 && (s_next != s_cur || keep_zero)) {
                 float a = __fdiv_rn(__fsub_rn(s_cur, s_next), s_cur);
@@ -888,10 +926,15 @@ cudaError_t run_march(const GridDev &g, const float *pinv, int V, int H, int W, 
     }
     if (mode == CNRMA_MARCH_DEPTH)
         march_depth_kernel<<<(unsigned)ws.blocks, kRayThreads, 0, stream>>>(p);
-    else if (p.cell != nullptr)
-        march_neus_kernel<true><<<(unsigned)ws.blocks, kRayThreads, 0, stream>>>(p);
-    else
-        march_neus_kernel<false><<<(unsigned)ws.blocks, kRayThreads, 0, stream>>>(p);
+    else if (p.cell != nullptr) {
+        // voxels per sample along a unit direction; see the kernel's FINE note for the two measured points
+        const bool fine = tuning().march_jump >= 0 ? tuning().march_jump != 0 : t_one <= 0.75f * g.vs;
+        if (fine)
+            march_neus_kernel<true, true><<<(unsigned)ws.blocks, kRayThreads, 0, stream>>>(p);
+        else
+            march_neus_kernel<true, false><<<(unsigned)ws.blocks, kRayThreads, 0, stream>>>(p);
+    } else
+        march_neus_kernel<false, false><<<(unsigned)ws.blocks, kRayThreads, 0, stream>>>(p);
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
     scan_blocks_kernel<<<1, kScanThreads, 0, stream>>>(p.blk_rows, p.blk_wsum,

@@ -563,6 +563,21 @@ def test_march_prepass_fused_equals_unfused(cn, scene, monkeypatch):
     assert fused.shape == unfused.shape and torch.equal(fused, unfused)
 
 
+@pytest.mark.parametrize("grids", [60, 300, 900])
+def test_march_jump_rules_agree(cn, scene, grids, monkeypatch):
+    """The march's two jump rules (CNRMA_MARCH_JUMP=0 / 1) and the launcher's own pick give identical rows, from samples
+    that advance several voxels at a time (60 steps) to a fraction of one (900 steps)."""
+    sc = scene
+    p, f, t = _scene_tensors(sc)
+    args = (sc.voxel_dim, sc.voxel_size, sc.origin, sc.stride)
+    auto = cn.rma_points(p, f, t, *args, grids=grids, threshold=0.05)[0].clone()
+    for jump in ("0", "1"):
+        monkeypatch.setenv("CNRMA_MARCH_JUMP", jump)
+        cn.reload_tuning()
+        forced = cn.rma_points(p, f, t, *args, grids=grids, threshold=0.05)[0]
+        assert forced.shape == auto.shape and torch.equal(forced, auto), jump
+
+
 @pytest.mark.parametrize("channels,owners", [(8, 2), (16, 3), (128, 2), (256, 4)])
 def test_routed_stage_a_single_gpu_simulation(cn, channels, owners):
     """The view-sharded Stage A over peer memory (cnrma_aggregate_views_routed + cnrma_finalize_routed), with the

@@ -82,6 +82,33 @@ def test_random_scene_stage_a_with_view_culling(seed, slab, monkeypatch):
         assert np.array_equal(vol[0].cpu().numpy().view(np.uint32), ovol.view(np.uint32))
 
 
+@pytest.mark.parametrize("seed", range(int(os.environ.get("CNRMA_RANDOM_SEEDS", "24"))))
+@pytest.mark.parametrize("jump", ["0", "1"])
+def test_random_scene_march_jump_rules(seed, jump, monkeypatch):
+    """Both jump rules of the NeuS march (clearance only / clearance + the sample's position inside its voxel) forced on
+    every draw, whatever the launcher would pick: a jump that is one sample too long changes a kept set or a weight."""
+    import cnrma_b200 as cn
+    monkeypatch.setenv("CNRMA_MARCH_JUMP", jump)
+    s = _random_scene(np.random.default_rng(5000 + seed))
+    f = torch.from_numpy(s["feats"]).cuda().unsqueeze(1)
+    p = torch.from_numpy(s["projs"]).cuda().unsqueeze(1)
+    t = torch.from_numpy(s["tsdf"]).cuda()[None, None]
+    args = (s["dim"], s["vs"], s["origin"], s["stride"])
+    rows = cn.rma_points(p, f, t, *args, grids=s["N"], threshold=s["thr"], normalize=False)[0].cpu().numpy()
+    ref = oracle.aggregate_2d_features_ray_marching(s["projs"], s["feats"], s["tsdf"], *args, grids=s["N"],
+                                                    neus_threshold=s["thr"], normalize=False)
+    if ref is None:
+        assert rows.shape[0] == 0
+        return
+    if rows.shape != ref.shape:      # a kept-set difference is only legitimate inside the threshold band
+        near = np.abs(ref[:, 3] - np.float32(s["thr"])) <= 1e-5 * s["thr"]
+        assert abs(rows.shape[0] - ref.shape[0]) <= int(near.sum()), (rows.shape, ref.shape)
+        return
+    assert np.array_equal(rows[:, :3].view(np.uint32), ref[:, :3].view(np.uint32))
+    assert np.array_equal(rows[:, 4:].view(np.uint32), ref[:, 4:].view(np.uint32))
+    assert np.abs(rows[:, 3] - ref[:, 3]).max() <= 1e-5 * max(ref[:, 3].max(), 1e-3)
+
+
 @pytest.mark.parametrize("seed", range(8))
 def test_random_fusion(seed):
     """GT TSDF fusion kernel against the oracle on random frame sets (half frame by frame, half in one launch)."""
