@@ -339,14 +339,16 @@ __global__ void __launch_bounds__(kRayThreads, 6) march_neus_kernel(const __grid
             const float step_max = fmaxf(fmaxf(fabsf(d[0]), fabsf(d[1])), fabsf(d[2])) * p.t_one / p.g.vs;
             inv_step[0] = inv_step[1] = inv_step[2] = (step_max > 0.0f) ? 1.0f / step_max : 0.0f;
         }
-        const int n_steps = ray_is_finite(o, d) ? p.N : -1;   // non-finite rays keep nothing (see sample_voxel)
-
+        // non-finite rays keep nothing (see sample_voxel).  (The bound is p.N itself, a kernel constant: a per-ray bound
+        // was being re-derived from spilled values at every sample under the 40-register cap.)
+        const int n_steps = p.N;
+        int overflow = 0;
+        if (ray_is_finite(o, d)) {
         float T = 1.0f;
         float s_cur = 0.0f;   // sigmoid(-tsdf) of the current sample (set at i == 0)
         const float s_out = sigmoid_neg(1.0f);   // samples outside the grid read tsdf = 1.0 (rm.py:744)
         int vox_cur = -1;
         bool entered = false;
-        int overflow = 0;
         for (int i = 0; i <= n_steps; ++i) {
             int vox_next = -1;
             int skip_to = -1;
@@ -414,6 +416,7 @@ __global__ void __launch_bounds__(kRayThreads, 6) march_neus_kernel(const __grid
             // samples i+1 .. skip_to all round to voxels that hold s_cur, so alpha == 0 and nothing
             // changes; resume with sample skip_to + 1 (never past the repeated last sample)
             if (skip_to > i) i = min(skip_to, p.N - 1);
+        }
         }
         p.counts[ray] = kept;
         if (overflow) atomicAdd(&p.result->overflow, 1);
