@@ -1,4 +1,5 @@
-"""Host time per scene of the public calls (aggregate_views + rma_points) against the GPU time of the same loop: where the host\nthread is busy, where it waits for M (the march result), and whether anything is left between steps.  Run under gpurun."""
+"""Host time per scene of the public calls (aggregate_views + rma_points) against the GPU time of the same loop: where the host
+thread is busy, where it waits for M (the march result), and whether anything is left between steps.  Run under gpurun."""
 import os, sys, time
 sys.path.insert(0, ".")
 import numpy as np, torch, cnrma_b200 as cn
