@@ -344,79 +344,79 @@ __global__ void __launch_bounds__(kRayThreads, 6) march_neus_kernel(const __grid
         const int n_steps = p.N;
         int overflow = 0;
         if (ray_is_finite(o, d)) {
-        float T = 1.0f;
-        float s_cur = 0.0f;   // sigmoid(-tsdf) of the current sample (set at i == 0)
-        const float s_out = sigmoid_neg(1.0f);   // samples outside the grid read tsdf = 1.0 (rm.py:744)
-        int vox_cur = -1;
-        bool entered = false;
-        for (int i = 0; i <= n_steps; ++i) {
-            int vox_next = -1;
-            int skip_to = -1;
-            float s_next = s_cur;   // i == N: last sample repeated (rm.py:758); same voxel -> same value
-            if (i < p.N) {
-                // the clearance is re-read at every sample: keeping it in a register while the voxel is unchanged was
-                // measured and is slower (cfg 2 march phase 0.350 -> 0.383 ms, cfg 1 0.244 -> 0.264 ms: the load hits L1 and
-                // the extra live register / select costs more than it saves)
-                if (SKIP && FINE) {
-                    int ix, iy, iz;
-                    float frac[3];
-                    vox_next = sample_voxel(p.g, vm, o, d, __fmul_rn((float)i, p.t_one), ix, iy, iz, frac);
-                    s_next = s_out;
-                    if (vox_next >= 0) {
-                        const uint2 c = __ldg(p.cell + vox_next);
-                        s_next = __uint_as_float(c.x);
-                        // Clearance k: every voxel within k of this one (L-infinity) holds the same s.  Sample i + j sits at
-                        // frac_a + j * step_a from this voxel's centre; while that stays below k + 0.5 - margin on every axis
-                        // it rounds to a voxel inside that cube (for k = 0: to this very voxel) and reads the same s.
-                        const float room = (float)c.y + (0.5f - kSkipMargin);
-                        float n = __fmaf_rn(-frac[0], inv_step[0], room * fabsf(inv_step[0]));
-                        n = fminf(n, __fmaf_rn(-frac[1], inv_step[1], room * fabsf(inv_step[1])));
-                        n = fminf(n, __fmaf_rn(-frac[2], inv_step[2], room * fabsf(inv_step[2])));
-                        skip_to = i + (int)n;   // n < 1 (or negative): no jump
-                    }
-                } else if (SKIP) {
-                    vox_next = sample_voxel(p.g, vm, o, d, __fmul_rn((float)i, p.t_one));
-                    s_next = s_out;
-                    if (vox_next >= 0) {
-                        const uint2 c = __ldg(p.cell + vox_next);
-                        s_next = __uint_as_float(c.x);
-                        // wherever the sample sits in its voxel (at most 0.5 from the centre), the next
-                        // floor((k - margin) / step) samples stay inside the cube of clearance k
-                        if (c.y > 0) skip_to = i + (int)(((float)c.y - kSkipMargin) * inv_step[0]);
-                    }
-                } else {
-                    vox_next = sample_voxel(p.g, vm, o, d, __fmul_rn((float)i, p.t_one));
-                    if (i == 0 || vox_next != vox_cur) s_next = (vox_next >= 0) ? __ldg(p.sig + vox_next) : s_out;
-                }
-            }
-            if (i > 0 && (s_next != s_cur || keep_zero)) {
-                float a = __fdiv_rn(__fsub_rn(s_cur, s_next), s_cur);
-                a = (a < 0.0f) ? 0.0f : a;   // clamp(min=0), NaN-propagating like torch
-                const float w = __fmul_rn(T, a);
-                if (vox_cur >= 0 && w >= p.thr) {
-                    if (kept < p.cap) {
-                        p.rec_w[(int64_t)kept * p.rays + ray] = w;
-                        p.rec_i[(int64_t)kept * p.rays + ray] = (float)(i - 1);
-                        wsum += (double)w;
-                        ++kept;
+            float T = 1.0f;
+            float s_cur = 0.0f;   // sigmoid(-tsdf) of the current sample (set at i == 0)
+            const float s_out = sigmoid_neg(1.0f);   // samples outside the grid read tsdf = 1.0 (rm.py:744)
+            int vox_cur = -1;
+            bool entered = false;
+            for (int i = 0; i <= n_steps; ++i) {
+                int vox_next = -1;
+                int skip_to = -1;
+                float s_next = s_cur;   // i == N: last sample repeated (rm.py:758); same voxel -> same value
+                if (i < p.N) {
+                    // the clearance is re-read at every sample: keeping it in a register while the voxel is unchanged was
+                    // measured and is slower (cfg 2 march phase 0.350 -> 0.383 ms, cfg 1 0.244 -> 0.264 ms: the load hits L1 and
+                    // the extra live register / select costs more than it saves)
+                    if (SKIP && FINE) {
+                        int ix, iy, iz;
+                        float frac[3];
+                        vox_next = sample_voxel(p.g, vm, o, d, __fmul_rn((float)i, p.t_one), ix, iy, iz, frac);
+                        s_next = s_out;
+                        if (vox_next >= 0) {
+                            const uint2 c = __ldg(p.cell + vox_next);
+                            s_next = __uint_as_float(c.x);
+                            // Clearance k: every voxel within k of this one (L-infinity) holds the same s.  Sample i + j sits at
+                            // frac_a + j * step_a from this voxel's centre; while that stays below k + 0.5 - margin on every axis
+                            // it rounds to a voxel inside that cube (for k = 0: to this very voxel) and reads the same s.
+                            const float room = (float)c.y + (0.5f - kSkipMargin);
+                            float n = __fmaf_rn(-frac[0], inv_step[0], room * fabsf(inv_step[0]));
+                            n = fminf(n, __fmaf_rn(-frac[1], inv_step[1], room * fabsf(inv_step[1])));
+                            n = fminf(n, __fmaf_rn(-frac[2], inv_step[2], room * fabsf(inv_step[2])));
+                            skip_to = i + (int)n;   // n < 1 (or negative): no jump
+                        }
+                    } else if (SKIP) {
+                        vox_next = sample_voxel(p.g, vm, o, d, __fmul_rn((float)i, p.t_one));
+                        s_next = s_out;
+                        if (vox_next >= 0) {
+                            const uint2 c = __ldg(p.cell + vox_next);
+                            s_next = __uint_as_float(c.x);
+                            // wherever the sample sits in its voxel (at most 0.5 from the centre), the next
+                            // floor((k - margin) / step) samples stay inside the cube of clearance k
+                            if (c.y > 0) skip_to = i + (int)(((float)c.y - kSkipMargin) * inv_step[0]);
+                        }
                     } else {
-                        overflow = 1;
+                        vox_next = sample_voxel(p.g, vm, o, d, __fmul_rn((float)i, p.t_one));
+                        if (i == 0 || vox_next != vox_cur) s_next = (vox_next >= 0) ? __ldg(p.sig + vox_next) : s_out;
                     }
                 }
-                T = __fmul_rn(T, __fsub_rn(1.0f, a));
-                // exact early exit: every later weight is <= T < thr
-                if ((SKIP || p.thr > 0.0f) && T < p.thr) break;
+                if (i > 0 && (s_next != s_cur || keep_zero)) {
+                    float a = __fdiv_rn(__fsub_rn(s_cur, s_next), s_cur);
+                    a = (a < 0.0f) ? 0.0f : a;   // clamp(min=0), NaN-propagating like torch
+                    const float w = __fmul_rn(T, a);
+                    if (vox_cur >= 0 && w >= p.thr) {
+                        if (kept < p.cap) {
+                            p.rec_w[(int64_t)kept * p.rays + ray] = w;
+                            p.rec_i[(int64_t)kept * p.rays + ray] = (float)(i - 1);
+                            wsum += (double)w;
+                            ++kept;
+                        } else {
+                            overflow = 1;
+                        }
+                    }
+                    T = __fmul_rn(T, __fsub_rn(1.0f, a));
+                    // exact early exit: every later weight is <= T < thr
+                    if ((SKIP || p.thr > 0.0f) && T < p.thr) break;
+                }
+                // exact early exit: the grid is convex and the rounded sample ids are monotone along the ray, so once
+                // left it is never re-entered, and samples outside are never kept
+                if (entered && vox_next < 0) break;
+                entered = entered || (vox_next >= 0);
+                s_cur = s_next;
+                vox_cur = vox_next;
+                // samples i+1 .. skip_to all round to voxels that hold s_cur, so alpha == 0 and nothing
+                // changes; resume with sample skip_to + 1 (never past the repeated last sample)
+                if (skip_to > i) i = min(skip_to, p.N - 1);
             }
-            // exact early exit: the grid is convex and the rounded sample ids are monotone along the ray, so once
-            // left it is never re-entered, and samples outside are never kept
-            if (entered && vox_next < 0) break;
-            entered = entered || (vox_next >= 0);
-            s_cur = s_next;
-            vox_cur = vox_next;
-            // samples i+1 .. skip_to all round to voxels that hold s_cur, so alpha == 0 and nothing
-            // changes; resume with sample skip_to + 1 (never past the repeated last sample)
-            if (skip_to > i) i = min(skip_to, p.N - 1);
-        }
         }
         p.counts[ray] = kept;
         if (overflow) atomicAdd(&p.result->overflow, 1);
